@@ -1,0 +1,67 @@
+// CPU emulation of one warp of the fused extractor: runs the per-lane phases of
+// seld_b200/csrc/extract_core.cuh lane by lane (a phase boundary is a __syncwarp() on the device).
+// TEST INFRASTRUCTURE: lets the CPU suite check the kernel's index math, tables and FFT against the
+// oracle without a GPU.  Built by tests/test_emu_cpu.py with g++ -std=c++17.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../seld_b200/csrc/extract_core.cuh"
+
+using namespace seld;
+
+template <int R, int MODE>
+static void run(const float* wav, int layout, int n_clips, long long L, int hop, int n_mels, const Tables& tb,
+                int T_out, float* out, float* clip_max) {
+    using G = Geo<R>;
+    const int C = (MODE == MODE_FOA) ? 7 : 10;
+    const int T_raw = 1 + int(L / hop);
+    std::vector<float2> E(G::E_ELEMS), S0(G::N), S1(G::N);
+    std::vector<float> acc(size_t(n_mels) * C, 0.f);
+    for (int clip = 0; clip < n_clips; ++clip) {
+        ClipSrc src;
+        src.base = wav + size_t(clip) * 4 * L;
+        src.n_samples = L;
+        if (layout == LAYOUT_PLANAR_CL) { src.chan_stride = L; src.samp_stride = 1; }
+        else { src.chan_stride = 1; src.samp_stride = 4; }
+        float cmax = -INFINITY;
+        const int T_tot = T_raw > T_out ? T_raw : T_out;
+        for (int t = 0; t < T_tot; ++t) {
+            float* row = (t < T_out) ? out + (size_t(clip) * T_out + t) * n_mels * C : nullptr;
+            if (t >= T_raw) { memset(row, 0, sizeof(float) * n_mels * C); continue; }
+            const long long start = (long long)t * hop - G::N / 2;
+            for (int l = 0; l < 32; ++l) stage1_forward<R>(src, 0, 1, start, tb, E.data(), l);
+            for (int l = 0; l < 32; ++l) stage2_forward<R>(E.data(), S0.data(), l);
+            for (int l = 0; l < 32; ++l) stage1_forward<R>(src, 2, 3, start, tb, E.data(), l);
+            for (int l = 0; l < 32; ++l) stage2_forward<R>(E.data(), S1.data(), l);
+            for (int l = 0; l < 32; ++l) bin_phase<R, MODE>(S0.data(), S1.data(), tb, acc.data(), n_mels, C, 1e-8f, l);
+            if (MODE == MODE_MIC) {
+                for (int l = 0; l < 32; ++l) gcc_stage1<R, 0>(S0.data(), S1.data(), E.data(), l);
+                for (int l = 0; l < 32; ++l) gcc_stage2<R, 0>(E.data(), tb, acc.data(), n_mels, C, l);
+                for (int l = 0; l < 32; ++l) gcc_stage1<R, 1>(S0.data(), S1.data(), E.data(), l);
+                for (int l = 0; l < 32; ++l) gcc_stage2<R, 1>(E.data(), tb, acc.data(), n_mels, C, l);
+                for (int l = 0; l < 32; ++l) gcc_stage1<R, 2>(S0.data(), S1.data(), E.data(), l);
+                for (int l = 0; l < 32; ++l) gcc_stage2<R, 2>(E.data(), tb, acc.data(), n_mels, C, l);
+            }
+            for (int l = 0; l < 32; ++l) cmax = fmaxf(cmax, finish_row(acc.data(), n_mels, C, row, l));
+        }
+        clip_max[clip] = cmax;
+    }
+}
+
+extern "C" int emu_extract(const float* wav, int layout, int n_clips, long long L, int n_fft, int hop, int n_mels,
+                           int mode, const float* window, const float* twiddle, const int* seg, const float* w0,
+                           const float* w1, int T_out, float* out, float* clip_max) {
+    Tables tb{window, reinterpret_cast<const float2*>(twiddle), seg, w0, w1};
+#define GO(RR)                                                                                             \
+    if (n_fft == 32 * RR) {                                                                                \
+        if (mode == MODE_FOA) run<RR, MODE_FOA>(wav, layout, n_clips, L, hop, n_mels, tb, T_out, out, clip_max); \
+        else run<RR, MODE_MIC>(wav, layout, n_clips, L, hop, n_mels, tb, T_out, out, clip_max);            \
+        return 0;                                                                                          \
+    }
+    GO(8) GO(16) GO(32) GO(64)
+    return -1;
+}
+
+extern "C" float emu_key_roundtrip(float f) { return key_to_float(float_to_key(f)); }
