@@ -1,0 +1,164 @@
+/*
+ * seld_b200 -- C ABI of the B200-native (sm_100a) SELD feature-extraction hot path.
+ *
+ * The reference (IRIS-AUDIO/SELD) has no FFI layer: its boundary is the Python module surface of
+ * feature_extractor.py / transforms.py.  seld_b200/feature_extractor.py and seld_b200/transforms.py
+ * keep that surface and call the entry points below through ctypes.  Each entry point cites the
+ * reference code it replaces (file:line relative to the reference repository).
+ *
+ * Conventions
+ *   - every pointer named *_dev is DEVICE memory owned by the caller; the library never frees it;
+ *   - every function returns 0 on success, a negative SELD_E* code on failure; seld_last_error()
+ *     returns the message of the calling thread's last failure;
+ *   - all work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t passed as void*);
+ *     nothing synchronises the device except seld_plan_create;
+ *   - plans are immutable after creation => entry points are re-entrant across threads and streams;
+ *   - there is NO CPU fallback: without an sm_100 device seld_plan_create fails with SELD_ENODEVICE.
+ */
+#ifndef SELD_B200_H
+#define SELD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SELD_OK 0
+#define SELD_EINVAL (-1)     /* bad argument */
+#define SELD_ENODEVICE (-2)  /* no sm_100 CUDA device */
+#define SELD_ECUDA (-3)      /* CUDA runtime error (message in seld_last_error) */
+#define SELD_EUNSUPPORTED (-4)
+
+#define SELD_MODE_FOA 0 /* 4 log-mel + 3 intensity-vector channels  (reference feature_extractor.py:74-77) */
+#define SELD_MODE_MIC 1 /* 4 log-mel + 6 GCC-PHAT channels           (reference feature_extractor.py:78-80) */
+
+#define SELD_LAYOUT_PLANAR_CL 0      /* wav[clip][chan][sample]  (torchaudio.load layout, feature_extractor.py:43) */
+#define SELD_LAYOUT_INTERLEAVED_LC 1 /* wav[clip][sample][chan]  (one 128-bit load = one time step of 4 channels) */
+
+#define SELD_RNG_PHILOX_COUNTER 0   /* Philox4x32-10, counter = (sample, axis slot, chunk, 2*mask+draw) */
+#define SELD_RNG_TF_EAGER_COMPAT 1  /* TensorFlow-2 eager op-seed stream (reproduces transforms_test.py:8-30) */
+
+#define SELD_DTYPE_F32 0
+#define SELD_DTYPE_F64 1
+#define SELD_DTYPE_F16 2
+#define SELD_DTYPE_BF16 3
+#define SELD_DTYPE_I32 4
+#define SELD_DTYPE_I64 5
+#define SELD_DTYPE_I16 6
+#define SELD_DTYPE_U8 7
+
+typedef struct seld_plan* seld_plan_t;
+
+#if defined(__GNUC__)
+#define SELD_API __attribute__((visibility("default")))
+#else
+#define SELD_API
+#endif
+
+SELD_API const char* seld_last_error(void);
+SELD_API int seld_version(void);
+
+/* 0 if device `device` (or the current one when < 0) is compute capability 10.x, else SELD_ENODEVICE. */
+SELD_API int seld_device_check(int device);
+
+/*
+ * Build an extraction plan: uploads the analysis window, FFT twiddles and the sparse form of the mel bank.
+ * Replaces the per-file constants of reference feature_extractor.py:59-60 (MelScale) and :167 (Hann window).
+ *   window_host  [n_fft]                 float32 window already zero-padded/centred to n_fft
+ *   mel_fb_host  [(n_fft/2+1) * n_mels]  dense float32 filterbank (row = STFT bin); each row may hold at
+ *                                        most two non-zeros, in adjacent filters (true of triangular banks)
+ *   n_fft in {256, 512, 1024, 2048}; n_chan must be 4; n_mels even for SELD_MODE_MIC.
+ */
+SELD_API int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length, int n_mels, int n_chan, int mode,
+                     const float* window_host, const float* mel_fb_host, seld_plan_t* plan_out);
+SELD_API int seld_plan_destroy(seld_plan_t plan);
+
+/* Output channels per (frame, mel): 7 (FOA) or 10 (MIC). */
+SELD_API int seld_plan_out_channels(seld_plan_t plan);
+/* Number of STFT frames of an n_samples-long clip: 1 + n_samples / hop  (torch.stft, center=True). */
+SELD_API int64_t seld_plan_num_frames(seld_plan_t plan, int64_t n_samples);
+
+/*
+ * Fused extractor: reference feature_extractor.py:53-88 (extract_features) + the feature half of :117-149
+ * (pad / truncate to t_out frames), batched over clips.
+ *   wav_dev            [n_clips][4][n_samples] (PLANAR_CL) or [n_clips][n_samples][4] (INTERLEAVED_LC) float32
+ *   feat_raw_dev       [n_clips][t_out][n_mels][C] float32; log-mel channels are written WITHOUT the top_db
+ *                      clamp (it needs the clip-global maximum); rows >= 1 + n_samples/hop are zero
+ *   clip_max_key_dev   [n_clips] uint32 order-preserving keys of the per-clip maximum dB over ALL frames
+ *                      (including frames >= t_out, as the reference takes the max before truncating);
+ *                      reset by this call; decode with seld_clip_max_decode
+ */
+SELD_API int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips, int64_t n_samples, int t_out,
+                 float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream);
+
+SELD_API int seld_clip_max_decode(const uint32_t* clip_max_key_dev, int n_clips, float* clip_max_dev, void* stream);
+
+/*
+ * top_db clamp (torchaudio amplitude_to_DB top_db=80, reference feature_extractor.py:65-71) fused with the
+ * per-file normaliser of reference feature_extractor.py:226-234:
+ *     y = max(x, clip_max - top_db)   on the 4 log-mel channels of rows < t_valid
+ *     y = (y - mean) / max(std, eps)  when mean_dev/std_dev are non-NULL ([n_mels][C] float32)
+ * clip_max_key_dev may be NULL (no clamp: input already clamped).  feat_out_dev may alias feat_in_dev.
+ */
+SELD_API int seld_finalize(int n_mels, int n_ch, const float* feat_in_dev, const uint32_t* clip_max_key_dev, int n_clips, int t_out,
+                  int t_valid, float top_db, const float* mean_dev, const float* std_dev, float eps,
+                  float* feat_out_dev, void* stream);
+
+/*
+ * Per-(mel, chan) partial statistics of reference feature_extractor.py:218-223 (calculate_statistics), with the
+ * top_db clamp applied on the fly, accumulated in float64 in a fixed order (run-to-run deterministic):
+ *     acc_dev[0 .. n)      += sum x        n = n_mels * C
+ *     acc_dev[n .. 2n)     += sum x^2
+ *     acc_dev[2n]          += number of rows (n_clips * t_out)
+ * acc_dev is ADDED to (zero it first); the caller all-reduces acc_dev across ranks (NCCL sum) and then calls
+ * seld_stats_finish.  workspace_dev: at least seld_stats_workspace_doubles(n_mels, n_ch) doubles.
+ * n_ch = C (7 | 10 | any layout whose first 4 channels per mel are the log-mel ones).
+ */
+SELD_API int64_t seld_stats_workspace_doubles(int n_mels, int n_ch);
+SELD_API int seld_stats(int n_mels, int n_ch, const float* feat_dev, const uint32_t* clip_max_key_dev, int n_clips, int t_out,
+               int t_valid, float top_db, double* workspace_dev, double* acc_dev, void* stream);
+/* mean = sum/n_rows, std = sqrt(max(sumsq/n_rows - mean^2, 0)) (population, ddof 0) -> float32 [n_mels][C]. */
+SELD_API int seld_stats_finish(int n_mels, int n_ch, const double* acc_dev, float* mean_dev, float* std_dev, void* stream);
+
+/*
+ * Fused time / frequency spectrogram masking, in place: reference transforms.py:6-43 (mask, period-wise) and
+ * :46-75 (simple_mask, one chunk).  x_dev is viewed as x[n_samples][t][mid][f][c] elements of `dtype`:
+ *   time masks   zero bands of rows inside each chunk of `period` rows of t   (total = period)
+ *   freq masks   zero bands of the f axis, drawn independently per chunk       (total = f)
+ * (any axis of any-rank input folds onto this view: axis 0 -> time; axis a > 0 -> mid = prod(shape[1:a]),
+ * f = shape[a], c = prod(shape[a+1:]);  simple_mask -> period <= 0, meaning one chunk spanning all of t.)
+ * Masked elements are MULTIPLIED by zero (float: -0.0 / NaN survive, as in the reference's x * mask); only
+ * masked elements are read or written.  Per chunk and mask: size in [0, max), offset in [0, total - size),
+ * time masks first, then freq masks (list order of reference train.py:157-160).  *_max <= 0 means "None"
+ * (= total); *_n == 0 disables that axis.  Fails with SELD_EINVAL when t % period != 0 (transforms.py:38-39).
+ *   rng_mode PHILOX_COUNTER   Philox4x32-10, key = seed, counter = (lo32(s), hi32(s), chunk,
+ *                             axis << 24 | mask << 1 | draw) with s = sample_offset + sample, axis 0 = time,
+ *                             1 = freq, draw 0 = size, 1 = offset
+ *   rng_mode TF_EAGER_COMPAT  TensorFlow-2 eager stream: `seed` = kernel seed (graph seed mod 2^31-1),
+ *                             op_seed2_dev[((sample * n_chunks + chunk) * n_masks + mask) * 2 + draw] = the op's
+ *                             seed2, generated on the host in draw order
+ *   draws_out_dev (nullable)  [n_samples][n_chunks][time_n + freq_n][2] int32 (offset, size)
+ */
+SELD_API int seld_mask(void* x_dev, int dtype, int64_t n_samples, int64_t t, int64_t mid, int64_t f, int64_t c, int period,
+              int time_max, int time_n, int freq_max, int freq_n, uint64_t seed, uint64_t sample_offset, int rng_mode,
+              const int64_t* op_seed2_dev, int32_t* draws_out_dev, void* stream);
+
+/*
+ * Stand-alone stages (API parity with the reference's public helpers; the hot path is seld_extract).
+ *   seld_complex_spec     reference feature_extractor.py:153-173; spec_dev [n_chan][T][F] complex64 (frame-major;
+ *                         the Python wrapper returns the [C, F, T] transposed view)
+ *   seld_foa_iv           reference feature_extractor.py:176-193; spec [4][n] complex64 -> iv [3][n]
+ *   seld_gcc              reference feature_extractor.py:196-214; spec [n_chan][T][F] complex64 (frame-major)
+ *                         -> gcc [pairs][n_lags][T] float32, row j = lag first_lag + j of the length-2(F-1) irfft
+ */
+SELD_API int seld_complex_spec(seld_plan_t plan, const float* wav_dev, int n_chan, int64_t n_samples, float scale,
+                      float* spec_dev, void* stream);
+SELD_API int seld_foa_iv(const float* spec_dev, int64_t n, float eps, float* iv_dev, void* stream);
+SELD_API int seld_gcc(const float* spec_dev, int n_chan, int64_t n_frames, int n_bins, int n_lags, int first_lag, float* gcc_dev,
+             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELD_B200_H */

@@ -63,13 +63,23 @@ class TFEagerRandom:
 
 
 class CounterRandom:
-    """The product's own stream: Philox4x32-10 keyed by the 64-bit seed, counter =
-    (sample, axis_slot, chunk, 2*mask_i + draw); draw 0 = size, draw 1 = offset.
-    Mirrors seld_b200/csrc/mask.cu (rng_mode PHILOX_COUNTER)."""
+    """The product's own stream (rng_mode PHILOX_COUNTER of seld_mask, seld_b200/csrc/mask.cu): Philox4x32-10
+    keyed by the 64-bit seed, counter = (lo32(s), hi32(s), chunk, axis << 24 | mask << 1 | draw) with
+    s = global sample index, axis 0 = time / 1 = freq, draw 0 = size / 1 = offset."""
 
     def __init__(self, seed: int):
         self.key = (seed & MASK32, (seed >> 32) & MASK32)
 
-    def u32(self, sample: int, axis_slot: int, chunk: int, mask_i: int, draw: int) -> int:
-        return philox4x32_10((sample & MASK32, axis_slot & MASK32, chunk & MASK32,
-                              (2 * mask_i + draw) & MASK32), self.key)[0]
+    def u32(self, sample: int, axis: int, chunk: int, mask_i: int, draw: int) -> int:
+        c3 = ((axis & 0xFF) << 24) | ((mask_i << 1) & 0xFFFFFF) | (draw & 1)
+        return philox4x32_10((sample & MASK32, (sample >> 32) & MASK32, chunk & MASK32, c3), self.key)[0]
+
+    def drawer(self, sample: int, axis: int, chunk: int):
+        """-> draw(maxval) callable yielding size, offset, size, offset, ... for successive masks."""
+        state = {'i': 0}
+
+        def draw(maxval: int) -> int:
+            i = state['i']
+            state['i'] += 1
+            return self.u32(sample, axis, chunk, i // 2, i % 2) % maxval
+        return draw

@@ -1,0 +1,385 @@
+// Fused STFT -> log-mel + intensity-vector / GCC-PHAT extractor, sm_100a.
+//
+// Replaces reference feature_extractor.py:53-88 (extract_features) and the feature half of :117-149
+// (pad / truncate), batched over clips.  One warp owns one STFT frame of all four channels; see
+// extract_core.cuh for the per-warp algorithm.  Persistent CTAs (one per SM, limited by shared memory)
+// walk super-chunks of consecutive frames so that the 2.13x overlap between neighbouring frames is served
+// by L1/L2 and HBM sees every sample once.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "extract_core.cuh"
+#include "plan.h"
+
+namespace seld {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return SELD_ECUDA;
+}
+
+struct ExtractArgs {
+    const float* wav;
+    int layout;
+    int n_clips;
+    long long n_samples;
+    int t_raw, t_out, t_tot;
+    float* out;
+    unsigned int* clip_max_key;
+    const float* window;
+    const float2* twiddle;
+    const int* seg;
+    const float* w0;
+    const float* w1;
+    int hop, n_mels, n_out_ch;
+    long long n_super;        // super-chunks of warps_per_cta * kFramesPerWarp frames
+};
+
+constexpr int kFramesPerWarp = 8;
+
+__host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
+
+template <int R>
+__host__ __device__ constexpr int table_bytes() {
+    using G = Geo<R>;
+    return align16(G::N * 4) + align16(G::N * 8) + 3 * align16(G::F * 4);
+}
+template <int R>
+__host__ __device__ constexpr int warp_bytes(int n_mels, int n_out_ch) {
+    using G = Geo<R>;
+    return align16(G::E_ELEMS * 8) + 2 * align16(G::N * 8) + align16(n_mels * n_out_ch * 4);
+}
+
+// register budget follows from the CTA size shared memory allows: 16 warps for n_fft <= 512, 8 for 1024, 4 for 2048
+template <int R>
+__host__ __device__ constexpr int max_warps() { return R <= 16 ? 16 : (R == 32 ? 8 : 4); }
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(ExtractArgs a) {
+    using G = Geo<R>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+
+    // ---- CTA-shared tables
+    unsigned char* p = smem;
+    float* s_window = reinterpret_cast<float*>(p);  p += align16(G::N * 4);
+    float2* s_twiddle = reinterpret_cast<float2*>(p);  p += align16(G::N * 8);
+    int* s_seg = reinterpret_cast<int*>(p);  p += align16(G::F * 4);
+    float* s_w0 = reinterpret_cast<float*>(p);  p += align16(G::F * 4);
+    float* s_w1 = reinterpret_cast<float*>(p);  p += align16(G::F * 4);
+    for (int i = threadIdx.x; i < G::N; i += blockDim.x) {
+        s_window[i] = a.window[i];
+        s_twiddle[i] = a.twiddle[i];
+    }
+    for (int i = threadIdx.x; i < G::F; i += blockDim.x) {
+        s_seg[i] = a.seg[i];
+        s_w0[i] = a.w0[i];
+        s_w1[i] = a.w1[i];
+    }
+    // ---- per-warp regions
+    const int wbytes = warp_bytes<R>(a.n_mels, a.n_out_ch);
+    unsigned char* wp = p + size_t(warp) * wbytes;
+    float2* E = reinterpret_cast<float2*>(wp);  wp += align16(G::E_ELEMS * 8);
+    float2* S0 = reinterpret_cast<float2*>(wp);  wp += align16(G::N * 8);
+    float2* S1 = reinterpret_cast<float2*>(wp);  wp += align16(G::N * 8);
+    float* acc = reinterpret_cast<float*>(wp);
+    const int row_elems = a.n_mels * a.n_out_ch;
+    for (int e = lane; e < row_elems; e += 32) acc[e] = 0.f;
+    __syncthreads();
+
+    const Tables tb{s_window, s_twiddle, s_seg, s_w0, s_w1};
+    const long long total_frames = (long long)a.n_clips * a.t_tot;
+
+    float run_max = -INFINITY;
+    int run_clip = -1;
+
+    for (long long sc = blockIdx.x; sc < a.n_super; sc += gridDim.x) {
+        const long long g0 = (sc * nwarps + warp) * kFramesPerWarp;
+        for (int i = 0; i < kFramesPerWarp; ++i) {
+            const long long g = g0 + i;
+            if (g >= total_frames) break;
+            const int clip = int(g / a.t_tot);
+            const int t = int(g - (long long)clip * a.t_tot);
+            float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
+            if (t >= a.t_raw) {                       // zero padding rows (reference :142-145)
+                for (int e = lane; e < row_elems; e += 32) row[e] = 0.f;
+                continue;
+            }
+            if (clip != run_clip) {
+                if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], float_to_key(run_max));
+                run_clip = clip;
+                run_max = -INFINITY;
+            }
+            ClipSrc src;
+            src.base = a.wav + (long long)clip * 4 * a.n_samples;
+            src.n_samples = a.n_samples;
+            if (a.layout == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
+            else { src.chan_stride = 1; src.samp_stride = 4; }
+            const long long start = (long long)t * a.hop - G::N / 2;
+
+            stage1_forward<R>(src, 0, 1, start, tb, E, lane);
+            __syncwarp();
+            stage2_forward<R>(E, S0, lane);
+            __syncwarp();
+            stage1_forward<R>(src, 2, 3, start, tb, E, lane);
+            __syncwarp();
+            stage2_forward<R>(E, S1, lane);
+            __syncwarp();
+            bin_phase<R, MODE>(S0, S1, tb, acc, a.n_mels, a.n_out_ch, 1e-8f, lane);
+            __syncwarp();
+            if constexpr (MODE == MODE_MIC) {
+                gcc_stage1<R, 0>(S0, S1, E, lane);
+                __syncwarp();
+                gcc_stage2<R, 0>(E, tb, acc, a.n_mels, a.n_out_ch, lane);
+                __syncwarp();
+                gcc_stage1<R, 1>(S0, S1, E, lane);
+                __syncwarp();
+                gcc_stage2<R, 1>(E, tb, acc, a.n_mels, a.n_out_ch, lane);
+                __syncwarp();
+                gcc_stage1<R, 2>(S0, S1, E, lane);
+                __syncwarp();
+                gcc_stage2<R, 2>(E, tb, acc, a.n_mels, a.n_out_ch, lane);
+                __syncwarp();
+            }
+            float mx = finish_row(acc, a.n_mels, a.n_out_ch, row, lane);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            run_max = fmaxf(run_max, mx);
+            __syncwarp();
+        }
+    }
+    if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], float_to_key(run_max));
+}
+
+__global__ void clip_max_decode_kernel(const unsigned int* keys, int n, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = key_to_float(keys[i]);
+}
+
+template <int R>
+static int launch_extract(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
+    const int threads = plan->warps_per_cta * 32;
+    if (plan->mode == SELD_MODE_FOA) {
+        SELD_CUDA_TRY(cudaFuncSetAttribute(extract_kernel<R, MODE_FOA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           plan->extract_smem_bytes));
+        extract_kernel<R, MODE_FOA><<<plan->grid, threads, plan->extract_smem_bytes, stream>>>(a);
+    } else {
+        SELD_CUDA_TRY(cudaFuncSetAttribute(extract_kernel<R, MODE_MIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           plan->extract_smem_bytes));
+        extract_kernel<R, MODE_MIC><<<plan->grid, threads, plan->extract_smem_bytes, stream>>>(a);
+    }
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
+template <int R>
+static void plan_geometry(seld_plan* plan) {
+    const int tb = table_bytes<R>();
+    const int wb = warp_bytes<R>(plan->n_mels, plan->n_out_ch);
+    int warps = (plan->max_smem_optin - tb) / wb;
+    if (warps > max_warps<R>()) warps = max_warps<R>();
+    plan->warps_per_cta = warps;
+    plan->extract_smem_bytes = tb + warps * wb;
+    plan->grid = plan->num_sms;
+}
+
+}  // namespace seld
+
+using namespace seld;
+
+extern "C" {
+
+const char* seld_last_error(void) { return g_last_error.c_str(); }
+int seld_version(void) { return 1; }
+
+int seld_device_check(int device) {
+    int dev = device;
+    if (dev < 0) {
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) { set_error(std::string("no CUDA device: ") + cudaGetErrorString(e)); return SELD_ENODEVICE; }
+    }
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) { set_error(std::string("no CUDA device: ") + cudaGetErrorString(e)); return SELD_ENODEVICE; }
+    if (prop.major != 10) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "seld_b200 needs an sm_100 (B200) device; device %d is sm_%d%d", dev, prop.major,
+                 prop.minor);
+        set_error(buf);
+        return SELD_ENODEVICE;
+    }
+    return SELD_OK;
+}
+
+int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length, int n_mels, int n_chan, int mode,
+                     const float* window_host, const float* mel_fb_host, seld_plan_t* plan_out) {
+    if (!plan_out || !window_host || !mel_fb_host) { set_error("null argument"); return SELD_EINVAL; }
+    *plan_out = nullptr;
+    if (n_fft != 256 && n_fft != 512 && n_fft != 1024 && n_fft != 2048) {
+        set_error("n_fft must be one of 256, 512, 1024, 2048");
+        return SELD_EUNSUPPORTED;
+    }
+    if (n_chan != 4) { set_error("the fused extractor needs exactly 4 channels"); return SELD_EUNSUPPORTED; }
+    if (mode != SELD_MODE_FOA && mode != SELD_MODE_MIC) { set_error("invalid mode"); return SELD_EINVAL; }
+    if (win_length <= 0 || win_length > n_fft || hop_length <= 0 || n_mels <= 0 || sample_rate <= 0) {
+        set_error("invalid STFT geometry");
+        return SELD_EINVAL;
+    }
+    if (mode == SELD_MODE_MIC && ((n_mels & 1) || n_mels > n_fft)) {
+        set_error("MIC mode needs an even n_mels <= n_fft (the reference concatenates n_mels GCC lags)");
+        return SELD_EINVAL;
+    }
+    int rc = seld_device_check(-1);
+    if (rc != SELD_OK) return rc;
+
+    seld_plan* plan = new seld_plan();
+    memset(plan, 0, sizeof(*plan));
+    plan->sample_rate = sample_rate;
+    plan->n_fft = n_fft;
+    plan->win_length = win_length;
+    plan->hop = hop_length;
+    plan->n_mels = n_mels;
+    plan->n_chan = n_chan;
+    plan->mode = mode;
+    plan->n_bins = n_fft / 2 + 1;
+    plan->n_out_ch = (mode == SELD_MODE_FOA) ? 7 : 10;
+    cudaGetDevice(&plan->device);
+    cudaDeviceGetAttribute(&plan->num_sms, cudaDevAttrMultiProcessorCount, plan->device);
+    cudaDeviceGetAttribute(&plan->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan->device);
+
+    // sparse form of the mel bank: <= 2 adjacent non-zeros per row
+    const int F = plan->n_bins;
+    std::vector<int> seg(F, -1);
+    std::vector<float> w0(F, 0.f), w1(F, 0.f);
+    for (int k = 0; k < F; ++k) {
+        int first = -1, count = 0, last = -1;
+        for (int m = 0; m < n_mels; ++m) {
+            if (mel_fb_host[(size_t)k * n_mels + m] != 0.f) {
+                if (first < 0) first = m;
+                last = m;
+                ++count;
+            }
+        }
+        if (count == 0) continue;
+        if (count > 2 || last - first > 1) {
+            delete plan;
+            set_error("mel filterbank row has more than two / non-adjacent non-zeros");
+            return SELD_EUNSUPPORTED;
+        }
+        seg[k] = first;
+        w0[k] = mel_fb_host[(size_t)k * n_mels + first];
+        if (count == 2) w1[k] = mel_fb_host[(size_t)k * n_mels + last];
+    }
+    std::vector<float> tw(2 * (size_t)n_fft);
+    for (int j = 0; j < n_fft; ++j) {
+        const double ang = -2.0 * 3.14159265358979323846264338327950288 * double(j) / double(n_fft);
+        tw[2 * j] = float(cos(ang));
+        tw[2 * j + 1] = float(sin(ang));
+    }
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void** dst, const void* src, size_t bytes) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc(dst, bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up((void**)&plan->window, window_host, sizeof(float) * n_fft);
+    up((void**)&plan->twiddle, tw.data(), sizeof(float) * 2 * n_fft);
+    up((void**)&plan->seg, seg.data(), sizeof(int) * F);
+    up((void**)&plan->w0, w0.data(), sizeof(float) * F);
+    up((void**)&plan->w1, w1.data(), sizeof(float) * F);
+    if (e != cudaSuccess) {
+        seld_plan_destroy(plan);
+        return cuda_fail(e, "plan table upload");
+    }
+    switch (n_fft) {
+        case 256: plan_geometry<8>(plan); break;
+        case 512: plan_geometry<16>(plan); break;
+        case 1024: plan_geometry<32>(plan); break;
+        default: plan_geometry<64>(plan); break;
+    }
+    if (plan->warps_per_cta < 1) {
+        seld_plan_destroy(plan);
+        set_error("n_mels too large for the shared-memory budget");
+        return SELD_EUNSUPPORTED;
+    }
+    plan->stats_blocks = plan->num_sms * 4;
+    *plan_out = plan;
+    return SELD_OK;
+}
+
+int seld_plan_destroy(seld_plan_t plan) {
+    if (!plan) return SELD_OK;
+    cudaFree(plan->window);
+    cudaFree(plan->twiddle);
+    cudaFree(plan->seg);
+    cudaFree(plan->w0);
+    cudaFree(plan->w1);
+    delete plan;
+    return SELD_OK;
+}
+
+int seld_plan_out_channels(seld_plan_t plan) { return plan ? plan->n_out_ch : SELD_EINVAL; }
+
+int64_t seld_plan_num_frames(seld_plan_t plan, int64_t n_samples) {
+    if (!plan || n_samples < 0) return SELD_EINVAL;
+    return 1 + n_samples / plan->hop;
+}
+
+int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips, int64_t n_samples, int t_out,
+                 float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream) {
+    if (!plan || !wav_dev || !feat_raw_dev || !clip_max_key_dev) { set_error("null argument"); return SELD_EINVAL; }
+    if (layout != SELD_LAYOUT_PLANAR_CL && layout != SELD_LAYOUT_INTERLEAVED_LC) { set_error("invalid layout"); return SELD_EINVAL; }
+    if (n_clips < 0 || t_out < 0) { set_error("negative size"); return SELD_EINVAL; }
+    if (n_samples <= plan->n_fft / 2) {
+        set_error("reflect padding needs n_fft/2 < number of samples (torch.stft raises here too)");
+        return SELD_EINVAL;
+    }
+    if (n_clips == 0) return SELD_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ExtractArgs a;
+    a.wav = wav_dev;
+    a.layout = layout;
+    a.n_clips = n_clips;
+    a.n_samples = n_samples;
+    a.t_raw = int(1 + n_samples / plan->hop);
+    a.t_out = t_out;
+    a.t_tot = a.t_raw > t_out ? a.t_raw : t_out;
+    a.out = feat_raw_dev;
+    a.clip_max_key = clip_max_key_dev;
+    a.window = plan->window;
+    a.twiddle = reinterpret_cast<const float2*>(plan->twiddle);
+    a.seg = plan->seg;
+    a.w0 = plan->w0;
+    a.w1 = plan->w1;
+    a.hop = plan->hop;
+    a.n_mels = plan->n_mels;
+    a.n_out_ch = plan->n_out_ch;
+    const long long per_super = (long long)plan->warps_per_cta * kFramesPerWarp;
+    a.n_super = ((long long)n_clips * a.t_tot + per_super - 1) / per_super;
+    SELD_CUDA_TRY(cudaMemsetAsync(clip_max_key_dev, 0, sizeof(uint32_t) * n_clips, st));
+    switch (plan->n_fft) {
+        case 256: return launch_extract<8>(plan, a, st);
+        case 512: return launch_extract<16>(plan, a, st);
+        case 1024: return launch_extract<32>(plan, a, st);
+        default: return launch_extract<64>(plan, a, st);
+    }
+}
+
+int seld_clip_max_decode(const uint32_t* clip_max_key_dev, int n_clips, float* clip_max_dev, void* stream) {
+    if (!clip_max_key_dev || !clip_max_dev || n_clips < 0) { set_error("bad argument"); return SELD_EINVAL; }
+    if (n_clips == 0) return SELD_OK;
+    clip_max_decode_kernel<<<(n_clips + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(clip_max_key_dev,
+                                                                                                  n_clips, clip_max_dev);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// Internal plan object shared by the .cu translation units (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/seld_b200.h"
+
+struct seld_plan {
+    int sample_rate, n_fft, win_length, hop, n_mels, n_chan, mode;
+    int n_bins;      // n_fft / 2 + 1
+    int n_out_ch;    // 7 | 10
+    int device;
+    int num_sms;
+    int max_smem_optin;
+    // device tables
+    float* window;   // [n_fft]
+    float* twiddle;  // [n_fft][2]
+    int* seg;        // [n_bins]
+    float* w0;       // [n_bins]
+    float* w1;       // [n_bins]
+    // extract launch geometry
+    int warps_per_cta;
+    int extract_smem_bytes;
+    int grid;
+    // stats launch geometry
+    int stats_blocks;
+};
+
+namespace seld {
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+}  // namespace seld
+
+#define SELD_CUDA_TRY(expr)                                          \
+    do {                                                             \
+        cudaError_t _e = (expr);                                     \
+        if (_e != cudaSuccess) return seld::cuda_fail(_e, #expr);    \
+    } while (0)

@@ -1,0 +1,223 @@
+// top_db clamp, dataset statistics and normalisation, sm_100a (HBM-bound streaming kernels).
+//
+//   seld_finalize      torchaudio amplitude_to_DB top_db clamp (reference feature_extractor.py:65-71) fused
+//                      with apply_normalizer's (x - mean) / max(std, eps) (reference :226-234)
+//   seld_stats         calculate_statistics (reference :218-223): per-(mel, chan) sum / sum of squares in
+//                      float64, fixed reduction order, clamp applied on the fly
+//   seld_stats_finish  mean / population std from the (all-reduced) accumulators
+#include <math.h>
+
+#include "plan.h"
+#include "seld_common.cuh"
+
+namespace seld {
+
+// ------------------------------------------------------------------ finalize
+// One thread per float4 (row length n_mels*C is a multiple of 4) or per scalar (VEC = 1).
+template <int VEC>
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ in, const unsigned int* __restrict__ keys,
+                                                        long long n_vec, int t_out, int t_valid, int row_len, int n_ch,
+                                                        float top_db, const float* __restrict__ mean,
+                                                        const float* __restrict__ stdv, float eps, float* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        const long long e = i * VEC;
+        const long long row = e / row_len;
+        const int p = int(e - row * row_len);
+        const int t = int(row % t_out);
+        float floor_db = -INFINITY;
+        if (keys != nullptr && t < t_valid) floor_db = key_to_float(keys[row / t_out]) - top_db;
+        float v[VEC];
+        if constexpr (VEC == 4) {
+            const float4 q = __ldcs(reinterpret_cast<const float4*>(in) + i);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+            v[0] = in[e];
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int c = (p + j) % n_ch;
+            if (c < 4) v[j] = fmaxf(v[j], floor_db);
+            if (mean != nullptr) v[j] = (v[j] - mean[p + j]) / fmaxf(stdv[p + j], eps);
+        }
+        if constexpr (VEC == 4) {
+            __stcs(reinterpret_cast<float4*>(out) + i, make_float4(v[0], v[1], v[2], v[3]));
+        } else {
+            out[e] = v[0];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ statistics
+// Block = G4 column groups (float4 each) x RP row phases.  Each thread owns 4 fixed (mel, chan) columns and
+// walks its block's row slab; partial sums stay in float64 registers, are folded over the row phases through
+// shared memory in a fixed order, and land in partials[block][2 * row_len].
+__global__ void __launch_bounds__(512) stats_partial_kernel(const float* __restrict__ x, const unsigned int* __restrict__ keys,
+                                                            long long n_rows, int t_out, int t_valid, int row_len, int n_ch,
+                                                            float top_db, int g4, int rp, double* __restrict__ partials) {
+    extern __shared__ double red[];   // [rp][2 * row_len]
+    const int g = threadIdx.x % g4;
+    const int ph = threadIdx.x / g4;
+    double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    if (ph < rp) {
+        const long long rows_per_block = (n_rows + gridDim.x - 1) / gridDim.x;
+        const long long r0 = (long long)blockIdx.x * rows_per_block;
+        long long r1 = r0 + rows_per_block;
+        if (r1 > n_rows) r1 = n_rows;
+        int cidx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cidx[j] = (4 * g + j) % n_ch;
+        for (long long r = r0 + ph; r < r1; r += rp) {
+            const int t = int(r % t_out);
+            float floor_db = -INFINITY;
+            if (keys != nullptr && t < t_valid) floor_db = key_to_float(keys[r / t_out]) - top_db;
+            const float4 v4 = __ldcs(reinterpret_cast<const float4*>(x + r * row_len) + g);
+            float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (cidx[j] < 4) v[j] = fmaxf(v[j], floor_db);
+                const double d = double(v[j]);
+                s[j] += d;
+                q[j] = fma(d, d, q[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            red[(size_t)ph * 2 * row_len + 4 * g + j] = s[j];
+            red[(size_t)ph * 2 * row_len + row_len + 4 * g + j] = q[j];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * row_len; i += blockDim.x) {
+        double a = 0.0;
+        for (int k = 0; k < rp; ++k) a += red[(size_t)k * 2 * row_len + i];
+        partials[(size_t)blockIdx.x * 2 * row_len + i] = a;
+    }
+}
+
+__global__ void stats_fold_kernel(const double* __restrict__ partials, int n_blocks, int n2, double n_rows,
+                                  double* __restrict__ acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n2) {
+        double a = 0.0;
+        for (int b = 0; b < n_blocks; ++b) a += partials[(size_t)b * n2 + i];
+        acc[i] += a;
+    }
+    if (i == 0) acc[n2] += n_rows;
+}
+
+// generic (row_len % 4 != 0) fallback: one thread per column, block-strided rows, same fixed-order fold
+__global__ void __launch_bounds__(256) stats_partial_scalar_kernel(const float* __restrict__ x, const unsigned int* __restrict__ keys,
+                                                                   long long n_rows, int t_out, int t_valid, int row_len,
+                                                                   int n_ch, float top_db, double* __restrict__ partials) {
+    const long long rows_per_block = (n_rows + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > n_rows) r1 = n_rows;
+    for (int p = threadIdx.x; p < row_len; p += blockDim.x) {
+        const bool logmel = (p % n_ch) < 4;
+        double s = 0, q = 0;
+        for (long long r = r0; r < r1; ++r) {
+            float v = x[r * row_len + p];
+            if (logmel && keys != nullptr && int(r % t_out) < t_valid) v = fmaxf(v, key_to_float(keys[r / t_out]) - top_db);
+            s += double(v);
+            q = fma(double(v), double(v), q);
+        }
+        partials[(size_t)blockIdx.x * 2 * row_len + p] = s;
+        partials[(size_t)blockIdx.x * 2 * row_len + row_len + p] = q;
+    }
+}
+
+__global__ void stats_finish_kernel(const double* __restrict__ acc, int n, float* __restrict__ mean, float* __restrict__ stdv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double cnt = acc[2 * n];
+        const double m = acc[i] / cnt;
+        double var = acc[n + i] / cnt - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[i] = float(m);
+        stdv[i] = float(sqrt(var));
+    }
+}
+
+}  // namespace seld
+
+using namespace seld;
+
+extern "C" {
+
+static int sm_count() {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+static int stats_block_count() { return sm_count() * 4; }
+
+int seld_finalize(int n_mels, int n_ch, const float* feat_in_dev, const uint32_t* clip_max_key_dev, int n_clips, int t_out,
+                  int t_valid, float top_db, const float* mean_dev, const float* std_dev, float eps, float* feat_out_dev,
+                  void* stream) {
+    if (!feat_in_dev || !feat_out_dev || n_mels < 1 || n_ch < 1) { set_error("bad argument"); return SELD_EINVAL; }
+    if ((mean_dev == nullptr) != (std_dev == nullptr)) { set_error("mean and std must be given together"); return SELD_EINVAL; }
+    if (n_clips < 0 || t_out < 0) { set_error("negative size"); return SELD_EINVAL; }
+    const int row_len = n_mels * n_ch;
+    const long long n = (long long)n_clips * t_out * row_len;
+    if (n == 0) return SELD_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = (row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat_in_dev) | reinterpret_cast<uintptr_t>(feat_out_dev)) % 16 == 0);
+    const long long n_vec = vec ? n / 4 : n;
+    long long blocks = (n_vec + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (vec)
+        finalize_kernel<4><<<(int)blocks, 256, 0, st>>>(feat_in_dev, clip_max_key_dev, n_vec, t_out, t_valid, row_len,
+                                                        n_ch, top_db, mean_dev, std_dev, eps, feat_out_dev);
+    else
+        finalize_kernel<1><<<(int)blocks, 256, 0, st>>>(feat_in_dev, clip_max_key_dev, n_vec, t_out, t_valid, row_len,
+                                                        n_ch, top_db, mean_dev, std_dev, eps, feat_out_dev);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
+int64_t seld_stats_workspace_doubles(int n_mels, int n_ch) {
+    if (n_mels < 1 || n_ch < 1) return SELD_EINVAL;
+    return (int64_t)stats_block_count() * 2 * n_mels * n_ch;
+}
+
+int seld_stats(int n_mels, int n_ch, const float* feat_dev, const uint32_t* clip_max_key_dev, int n_clips, int t_out,
+               int t_valid, float top_db, double* workspace_dev, double* acc_dev, void* stream) {
+    if (!feat_dev || !workspace_dev || !acc_dev || n_mels < 1 || n_ch < 1) { set_error("bad argument"); return SELD_EINVAL; }
+    if (n_clips < 0 || t_out < 0) { set_error("negative size"); return SELD_EINVAL; }
+    const int row_len = n_mels * n_ch;
+    const long long n_rows = (long long)n_clips * t_out;
+    if (n_rows == 0) return SELD_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int blocks = stats_block_count();
+    if (blocks > n_rows) blocks = (int)n_rows;
+    const int g4 = row_len / 4;
+    if (row_len % 4 == 0 && g4 <= 512 && reinterpret_cast<uintptr_t>(feat_dev) % 16 == 0) {
+        const int rp = 512 / g4;
+        const size_t smem = sizeof(double) * rp * 2 * row_len;
+        SELD_CUDA_TRY(cudaFuncSetAttribute(stats_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stats_partial_kernel<<<blocks, g4 * rp, smem, st>>>(feat_dev, clip_max_key_dev, n_rows, t_out, t_valid, row_len,
+                                                            n_ch, top_db, g4, rp, workspace_dev);
+    } else {
+        stats_partial_scalar_kernel<<<blocks, 256, 0, st>>>(feat_dev, clip_max_key_dev, n_rows, t_out, t_valid, row_len,
+                                                            n_ch, top_db, workspace_dev);
+    }
+    SELD_CUDA_TRY(cudaGetLastError());
+    const int n2 = 2 * row_len;
+    stats_fold_kernel<<<(n2 + 127) / 128, 128, 0, st>>>(workspace_dev, blocks, n2, double(n_rows), acc_dev);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
+int seld_stats_finish(int n_mels, int n_ch, const double* acc_dev, float* mean_dev, float* std_dev, void* stream) {
+    if (!acc_dev || !mean_dev || !std_dev || n_mels < 1 || n_ch < 1) { set_error("bad argument"); return SELD_EINVAL; }
+    const int n = n_mels * n_ch;
+    stats_finish_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(acc_dev, n, mean_dev, std_dev);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+"""Batched, device-resident form of the hot path (what bench.py measures).
+
+The reference walks files one at a time (feature_extractor.py:37-50), then concatenates the whole dataset on
+the CPU for mean/std (:218-223) and rewrites every file (:226-234).  Here a shard of clips lives in HBM:
+
+    feat, key = extract_batch(wav)                # fused STFT -> log-mel + IV | GCC, un-clamped dB + clip max
+    acc = partial_statistics(feat, key, t_valid)  # float64 per-bin sum / sum-of-squares, clamp on the fly
+    allreduce_statistics(acc)                     # the path's only collective (NCCL sum of <= 1281 doubles)
+    mean, std = finish_statistics(acc, n_mels, C)
+    finalize_(feat, key, t_valid, mean, std)      # top_db clamp + (x - mean) / max(std, eps), in place
+
+Every function enqueues on the current CUDA stream and returns without synchronising.
+"""
+import torch
+
+from . import _lib
+from .plan import get_plan
+
+TOP_DB = 80.0   # reference feature_extractor.py:70
+
+
+def _check_cuda_f32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise ValueError(f'{name} must be a contiguous float32 CUDA tensor')
+
+
+def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', out=None, **kwargs):
+    """wav: CUDA float32 [n_clips, 4, L] (layout='planar') or [n_clips, L, 4] ('interleaved').
+
+    Returns (feat_raw [n_clips, t_out, n_mels, C] float32, clip_max_key [n_clips] int32 keys).  Log-mel channels
+    are NOT yet clamped to clip_max - 80 dB: pass both to finalize_ / partial_statistics.
+    Replaces reference feature_extractor.py:53-88 + :140-147 for a batch of clips.
+    """
+    _check_cuda_f32(wav, 'wav')
+    if wav.dim() != 3:
+        raise ValueError('wav must be [n_clips, 4, L] or [n_clips, L, 4]')
+    if layout == 'planar':
+        n_clips, n_chan, n_samples = wav.shape
+        code = _lib.LAYOUT_PLANAR_CL
+    elif layout == 'interleaved':
+        n_clips, n_samples, n_chan = wav.shape
+        code = _lib.LAYOUT_INTERLEAVED_LC
+    else:
+        raise ValueError('layout must be "planar" or "interleaved"')
+    if n_chan != 4:
+        raise ValueError('the fused extractor needs exactly 4 channels')
+    pad = int(kwargs.pop('pad', 0))
+    if pad > 0:   # torchaudio spectrogram(pad=...): constant zero padding of the waveform before the STFT
+        dims = (pad, pad) if layout == 'planar' else (0, 0, pad, pad)
+        wav = torch.nn.functional.pad(wav, dims).contiguous()
+        n_samples += 2 * pad
+    with torch.cuda.device(wav.device):
+        plan = get_plan(sample_rate, mode=mode, n_mels=n_mels, **kwargs)
+        t_raw = plan.num_frames(n_samples)
+        if t_out is None:
+            t_out = t_raw
+        shape = (n_clips, int(t_out), plan.n_mels, plan.n_out_ch)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=wav.device)
+        else:
+            _check_cuda_f32(out, 'out')
+            if tuple(out.shape) != shape:
+                raise ValueError(f'out must have shape {shape}')
+        key = torch.empty(n_clips, dtype=torch.int32, device=wav.device)
+        _lib.check(_lib.load().seld_extract(plan.handle, _lib.ptr(wav), code, n_clips, n_samples, int(t_out),
+                                            _lib.ptr(out), _lib.ptr(key), _lib.current_stream_ptr()))
+    return out, key
+
+
+def clip_max_db(clip_max_key):
+    """Decode the per-clip maximum dB (float32 [n_clips])."""
+    out = torch.empty(clip_max_key.numel(), dtype=torch.float32, device=clip_max_key.device)
+    with torch.cuda.device(clip_max_key.device):
+        _lib.check(_lib.load().seld_clip_max_decode(_lib.ptr(clip_max_key), clip_max_key.numel(), _lib.ptr(out),
+                                                    _lib.current_stream_ptr()))
+    return out
+
+
+def _feat_dims(feat):
+    _check_cuda_f32(feat, 'feat')
+    if feat.dim() == 3:
+        feat = feat.unsqueeze(0)
+    if feat.dim() != 4:
+        raise ValueError('features must be [n_clips, T, n_mels, C]')
+    return feat, feat.shape
+
+
+def finalize_(feat, clip_max_key=None, t_valid=None, mean=None, std=None, eps=1e-8, top_db=TOP_DB, out=None):
+    """In place (or into `out`): top_db clamp of the log-mel channels of rows < t_valid, then optionally
+    (x - mean) / max(std, eps).  Reference feature_extractor.py:65-71 and :233."""
+    feat4, (n_clips, t_out, n_mels, n_ch) = _feat_dims(feat)
+    if t_valid is None:
+        t_valid = t_out
+    if out is None:
+        out = feat
+    if (mean is None) != (std is None):
+        raise ValueError('mean and std must be given together')
+    if mean is not None:
+        mean = mean.to(device=feat.device, dtype=torch.float32).reshape(-1).contiguous()
+        std = std.to(device=feat.device, dtype=torch.float32).reshape(-1).contiguous()
+        if mean.numel() != n_mels * n_ch or std.numel() != n_mels * n_ch:
+            raise ValueError('mean/std must have n_mels * C elements')
+    with torch.cuda.device(feat.device):
+        _lib.check(_lib.load().seld_finalize(n_mels, n_ch, _lib.ptr(feat4), _lib.ptr(clip_max_key), n_clips, t_out,
+                                             int(min(t_valid, t_out)), float(top_db), _lib.ptr(mean), _lib.ptr(std),
+                                             float(eps), _lib.ptr(out), _lib.current_stream_ptr()))
+    return out
+
+
+def new_accumulator(n_mels, n_ch, device):
+    return torch.zeros(2 * n_mels * n_ch + 1, dtype=torch.float64, device=device)
+
+
+def partial_statistics(feat, clip_max_key=None, t_valid=None, acc=None, top_db=TOP_DB):
+    """Add this shard's per-(mel, chan) {sum, sum of squares, row count} to `acc` (float64 [2*n_mels*C + 1])."""
+    feat4, (n_clips, t_out, n_mels, n_ch) = _feat_dims(feat)
+    if t_valid is None:
+        t_valid = t_out
+    if acc is None:
+        acc = new_accumulator(n_mels, n_ch, feat.device)
+    lib = _lib.load()
+    with torch.cuda.device(feat.device):
+        ws = torch.empty(lib.seld_stats_workspace_doubles(n_mels, n_ch), dtype=torch.float64, device=feat.device)
+        _lib.check(lib.seld_stats(n_mels, n_ch, _lib.ptr(feat4), _lib.ptr(clip_max_key), n_clips, t_out,
+                                  int(min(t_valid, t_out)), float(top_db), _lib.ptr(ws), _lib.ptr(acc),
+                                  _lib.current_stream_ptr()))
+    return acc
+
+
+def allreduce_statistics(acc):
+    """Sum the accumulators over all ranks (no-op without an initialised process group).  This is the path's only
+    collective: 2*64*C + 1 doubles (<= 10.2 KB) over NCCL / NVLink."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    return acc
+
+
+def finish_statistics(acc, n_mels, n_ch):
+    """(mean, std) float32 [1, n_mels, C] from the accumulators: population std, as numpy's in the reference."""
+    mean = torch.empty(1, n_mels, n_ch, dtype=torch.float32, device=acc.device)
+    std = torch.empty_like(mean)
+    with torch.cuda.device(acc.device):
+        _lib.check(_lib.load().seld_stats_finish(n_mels, n_ch, _lib.ptr(acc), _lib.ptr(mean), _lib.ptr(std),
+                                                 _lib.current_stream_ptr()))
+    return mean, std
+
+
+def extract_normalized_dataset(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', out=None, **kwargs):
+    """The reference's whole `__main__` (feature_extractor.py:294-307) for this rank's shard, in HBM:
+    extract -> statistics -> all-reduce -> normalise.  Returns (features, mean, std)."""
+    n_samples = wav.shape[2] if layout == 'planar' else wav.shape[1]
+    feat, key = extract_batch(wav, sample_rate, mode, n_mels, t_out, layout, out, **dict(kwargs))
+    t_raw = get_plan(sample_rate, mode=mode, n_mels=n_mels,
+                     **{k: v for k, v in kwargs.items() if k != 'pad'}).num_frames(n_samples + 2 * int(kwargs.get('pad', 0)))
+    acc = partial_statistics(feat, key, t_raw)
+    allreduce_statistics(acc)
+    mean, std = finish_statistics(acc, feat.shape[2], feat.shape[3])
+    finalize_(feat, key, t_raw, mean, std)
+    return feat, mean, std

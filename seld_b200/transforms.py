@@ -1,0 +1,172 @@
+"""Drop-in for the masking half of the reference's ``transforms`` module, computed on a B200.
+
+``mask`` and ``simple_mask`` keep the reference's names, argument order, defaults and error behaviour
+(transforms.py:6-43, :46-75); they accept numpy arrays or torch tensors and return a NEW array of the same kind,
+shape and dtype.  ``mask_batch_`` is the fused, in-place form for whole training batches (time and frequency
+masks of every sample in one kernel).
+
+Random streams
+  * ``set_seed(s)`` mirrors ``tf.random.set_seed(s)`` in eager mode: the next draws follow TensorFlow-2's stream
+    bit for bit (this is how the known answers of reference transforms_test.py:8-30 are reproduced).
+  * without it (the reference's own training runs never seed, and tf.data draws in a nondeterministic order --
+    there is nothing to reproduce) a process-wide counter-based Philox stream is used: draws are a pure function of
+    (seed, sample index, axis, chunk, mask, draw), so any batch can be re-generated.
+"""
+import os
+import random
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ['mask', 'simple_mask', 'mask_batch_', 'set_seed', 'set_counter_seed']
+
+_MAXINT32 = 2 ** 31 - 1
+_state = threading.local()
+_global_lock = threading.Lock()
+_counter = {'seed': int.from_bytes(os.urandom(8), 'little'), 'next_sample': 0}
+
+
+# --------------------------------------------------------------------------- random streams (host side)
+class _TFEagerStream:
+    """TensorFlow-2 eager seeding: graph seed g; every un-seeded op takes ``rng.randint(0, 2**31-1)`` from a
+    ``random.Random(g)``; kernel seeds are (g mod M, op mod M) with M = 2**31-1, (0, 0) -> (0, M)."""
+
+    def __init__(self, seed):
+        self.graph_seed = int(seed)
+        self._rng = random.Random(self.graph_seed)
+
+    def kernel_seed(self):
+        return self.graph_seed % _MAXINT32
+
+    def next_seed2(self):
+        op = self._rng.randint(0, _MAXINT32) % _MAXINT32
+        if self.kernel_seed() == 0 and op == 0:
+            op = _MAXINT32
+        return op
+
+
+def set_seed(seed):
+    """Like ``tf.random.set_seed``: subsequent ``mask`` / ``simple_mask`` calls on this thread follow TF's eager
+    stream.  ``set_seed(None)`` returns to the counter-based stream."""
+    _state.tf = None if seed is None else _TFEagerStream(seed)
+
+
+def set_counter_seed(seed, next_sample=0):
+    """Seed the process-wide counter-based stream (used when no TF-compatible seed is set)."""
+    with _global_lock:
+        _counter['seed'] = int(seed) & (2 ** 64 - 1)
+        _counter['next_sample'] = int(next_sample)
+
+
+def _take_samples(n):
+    with _global_lock:
+        first = _counter['next_sample']
+        _counter['next_sample'] += n
+        return _counter['seed'], first
+
+
+# --------------------------------------------------------------------------- kernel launch
+def _launch(x, n_samples, t, mid, f, c, period, time_max, time_n, freq_max, freq_n, seed, sample_offset, rng_mode,
+            op_seed2=None, want_draws=False):
+    code = _lib.DTYPE_CODES.get(str(x.dtype).replace('torch.', ''))
+    if code is None:
+        raise TypeError(f'unsupported dtype {x.dtype}')
+    n_chunks = 1 if period <= 0 else t // period
+    draws = None
+    if want_draws:
+        draws = torch.empty(n_samples, n_chunks, time_n + freq_n, 2, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().seld_mask(_lib.ptr(x), code, n_samples, t, mid, f, c, int(period),
+                                         int(time_max or 0), int(time_n), int(freq_max or 0), int(freq_n),
+                                         int(seed), int(sample_offset), rng_mode, _lib.ptr(op_seed2), _lib.ptr(draws),
+                                         _lib.current_stream_ptr()))
+    return draws
+
+
+def _to_cuda_copy(specs):
+    """-> (fresh contiguous CUDA tensor, restore(tensor) -> same kind as the input)."""
+    _lib.require_device()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    if isinstance(specs, torch.Tensor):
+        src_dev = specs.device
+        x = specs.to(dev).contiguous()
+        if x.data_ptr() == specs.data_ptr():
+            x = x.clone()
+        return x, (lambda y: y if src_dev.type == 'cuda' else y.to(src_dev))
+    arr = np.ascontiguousarray(specs)
+    return torch.from_numpy(arr.copy()).to(dev), (lambda y: y.cpu().numpy())
+
+
+def _single_axis(x, axis, max_mask_size, n_mask, period):
+    """Mask one axis of one sample through the reference-signature entry points."""
+    nd = x.dim()
+    ax = axis % nd if -nd <= axis < nd else None
+    if ax is None:
+        raise ValueError('axis out of range')
+    shape = list(x.shape)
+    n_mask = int(n_mask)
+    if period is not None and ax == 0:          # time masks inside each period-long chunk
+        t, mid, f, c = shape[0], 1, 1, int(np.prod(shape[1:], dtype=np.int64))
+        tm, tn, fm, fn, total = max_mask_size, n_mask, 0, 0, period
+    elif period is not None:                    # another axis, drawn independently per chunk of the time axis
+        t, mid, f, c = shape[0], int(np.prod(shape[1:ax], dtype=np.int64)), shape[ax], int(np.prod(shape[ax + 1:], dtype=np.int64))
+        tm, tn, fm, fn, total = 0, 0, max_mask_size, n_mask, shape[ax]
+    else:                                       # simple_mask: one chunk, everything before `axis` folds into mid
+        t, mid, f, c = 1, int(np.prod(shape[:ax], dtype=np.int64)), shape[ax], int(np.prod(shape[ax + 1:], dtype=np.int64))
+        tm, tn, fm, fn, total = 0, 0, max_mask_size, n_mask, shape[ax]
+    if max_mask_size is not None and not 0 < int(max_mask_size) <= total:
+        raise ValueError('max_mask_size must be in (0, axis length]')
+    if x.numel() == 0 or n_mask == 0:
+        return
+    per = period if period is not None else 0
+    n_chunks = 1 if per == 0 else t // per
+    tf = getattr(_state, 'tf', None)
+    if tf is not None:
+        seeds = [tf.next_seed2() for _ in range(n_chunks * n_mask * 2)]      # draw order: chunk, mask, (size, offset)
+        op_seed2 = torch.tensor(seeds, dtype=torch.int64, device=x.device)
+        _launch(x, 1, t, mid, f, c, per, tm, tn, fm, fn, tf.kernel_seed(), 0, _lib.RNG_TF_EAGER_COMPAT, op_seed2)
+    else:
+        seed, first = _take_samples(1)
+        _launch(x, 1, t, mid, f, c, per, tm, tn, fm, fn, seed, first, _lib.RNG_PHILOX_COUNTER)
+
+
+def mask(specs, axis, max_mask_size=None, period=100, n_mask=1):
+    """reference transforms.py:6-43: cut the time axis (axis 0) into ``period``-long chunks and, in each chunk
+    independently, zero ``n_mask`` random bands of ``axis``; size in [0, max_mask_size), offset in [0, total-size)."""
+    shape = tuple(specs.shape)
+    if shape[0] % period != 0:
+        raise ValueError("(spec time length / period)' rest must be 0")
+    x, restore = _to_cuda_copy(specs)
+    _single_axis(x, axis, max_mask_size, n_mask, int(period))
+    return restore(x)
+
+
+def simple_mask(specs, axis, max_mask_size=None, n_mask=1):
+    """reference transforms.py:46-75: ``n_mask`` random zero bands along ``axis`` of the whole array."""
+    x, restore = _to_cuda_copy(specs)
+    _single_axis(x, axis, max_mask_size, n_mask, None)
+    return restore(x)
+
+
+def mask_batch_(x, time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, sample_offset=None, return_draws=False):
+    """Fused in-place masking of a CUDA batch ``x[B, T, F, C]``: per sample and per ``period``-frame chunk,
+    ``time_mask = (max_size, n)`` bands of frames then ``freq_mask = (max_size, n)`` bands of mel bins -- the
+    ``sample_transforms`` of reference train.py:157-160 (24x1, 16x1) / trainv2.py:136-137 (6x10, 8x6) in one pass.
+    Draws depend only on (seed, sample_offset + b, axis, chunk, mask, draw)."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.is_contiguous() and x.dim() == 4):
+        raise ValueError('x must be a contiguous CUDA tensor [B, T, F, C]')
+    b, t, f, c = x.shape
+    if t % period != 0:
+        raise ValueError("(spec time length / period)' rest must be 0")
+    tm, tn = time_mask if time_mask else (0, 0)
+    fm, fn = freq_mask if freq_mask else (0, 0)
+    if seed is None:
+        seed, first = _take_samples(b)
+        sample_offset = first if sample_offset is None else sample_offset
+    elif sample_offset is None:
+        sample_offset = 0
+    return _launch(x, b, t, 1, f, c, int(period), tm, int(tn), fm, int(fn), int(seed) & (2 ** 64 - 1), int(sample_offset),
+                   _lib.RNG_PHILOX_COUNTER, None, return_draws)

@@ -1,0 +1,94 @@
+"""Parity of the fused CUDA extractor with the reference (golden vectors + oracle port), through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from cases import CASES, PROD, case_input, check_features, input_matches_golden, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def fe():
+    from seld_b200 import feature_extractor
+    return feature_extractor
+
+
+@pytest.mark.parametrize('name', list(CASES))
+@pytest.mark.parametrize('mode', ['foa', 'mic'])
+def test_golden_reference_outputs(fe, name, mode):
+    """Outputs of the UNMODIFIED reference (tests/golden, oracle/make_golden.py) on the same seeded inputs."""
+    wav, sr, n_mels, kw = case_input(name)
+    g = load_golden(name)
+    if not input_matches_golden(wav, g):
+        pytest.skip('synthetic input differs from the one the fixture was made with (torch RNG changed)')
+    got = fe.extract_features(wav, sr, mode=mode, n_mels=n_mels, **kw)
+    assert got.shape[0] == 1 + wav.shape[1] // (kw.get('hop_length') or (kw.get('win_length') or kw.get('n_fft', 512)) // 2)
+    check_features(got, g[mode], mode, f'{name}/{mode}')
+
+
+def test_reference_own_test_input(fe):
+    """reference feature_extractor_test.py:24-34 (zeros, 16 kHz, default kwargs) + the known answers behind it."""
+    wav = torch.zeros((4, 32000))
+    foa = fe.extract_features(wav, 16000, mode='foa')
+    assert foa.ndim == 3 and foa.shape == (126, 64, 7)
+    assert np.all(foa[..., :4] == -100.0) and np.all(foa[..., 4:] == 0.0)
+    mic = fe.extract_features(wav, 16000, mode='mic')
+    assert mic.ndim == 3 and mic.shape == (126, 64, 10)
+    assert np.all(mic[..., :4] == -100.0)
+    assert np.allclose(mic[:, 32, 4:], 1.0, atol=1e-6) and np.abs(np.delete(mic[..., 4:], 32, axis=1)).max() < 1e-6
+    with pytest.raises(ValueError):
+        fe.extract_features(wav, 16000, mode='bad')
+
+
+@pytest.mark.parametrize('mode', ['foa', 'mic'])
+@pytest.mark.parametrize('layout', ['planar', 'interleaved'])
+def test_batched_against_oracle(mode, layout):
+    """5 ragged-length-free clips in one launch, both input layouts, pad and truncate, vs the float32 oracle port."""
+    from oracle import extractor as O
+    from seld_b200 import pipeline
+    from seld_b200.synth import make_clips
+    n, L = 5, 50000
+    wav = make_clips(range(300, 300 + n), L)
+    dev = wav.cuda()
+    if layout == 'interleaved':
+        dev = dev.transpose(1, 2).contiguous()
+    t_raw = 1 + L // 480
+    for t_out in (t_raw, t_raw - 7, t_raw + 5):
+        feat, key = pipeline.extract_batch(dev, 24000, mode=mode, t_out=t_out, layout=layout, **PROD)
+        cmax = pipeline.clip_max_db(key).cpu().numpy()
+        pipeline.finalize_(feat, key, t_raw)
+        got = feat.cpu().numpy()
+        for i in range(n):
+            ref = O.extract_features_port(wav[i], 24000, mode=mode, **PROD)
+            assert abs(cmax[i] - ref[..., :4].max()) <= 1e-4            # max over ALL frames, also the truncated ones
+            want = O.preprocess_features_port(ref, max_label_length=t_out, multiplier=1)
+            check_features(got[i], want, mode, f'clip {i} t_out {t_out}')
+            if t_out > t_raw:
+                assert np.all(got[i, t_raw:] == 0.0)                    # zero padding rows stay exactly zero
+
+
+def test_short_clip_is_rejected(fe):
+    with pytest.raises(ValueError):
+        fe.extract_features(torch.zeros(4, 200), 16000)                 # reflect pad needs n_fft//2 < L
+
+
+def test_full_size_clip_properties():
+    """Production size (60 s, 4 ch, 24 kHz -> 3001 frames, saved 3000): frame count, layout, clamp floor, and
+    agreement with the oracle on the whole clip."""
+    from oracle import extractor as O
+    from seld_b200 import pipeline
+    from seld_b200.synth import make_clip
+    wav = make_clip(1000)
+    assert wav.shape == (4, 1_440_000)
+    for mode, c in (('foa', 7), ('mic', 10)):
+        feat, key = pipeline.extract_batch(wav.cuda().unsqueeze(0), 24000, mode=mode, t_out=3000, **PROD)
+        pipeline.finalize_(feat, key, 3001)
+        got = feat[0].cpu().numpy()
+        assert got.shape == (3000, 64, c)
+        ref = O.extract_features_port(wav, 24000, mode=mode, **PROD)
+        assert ref.shape == (3001, 64, c)
+        check_features(got, ref[:3000], mode, f'full {mode}')
+        floor = ref[..., :4].max() - 80.0
+        assert abs(got[..., :4].min() - floor) <= 1e-4                  # the clamp is active on this clip
+        assert (got[..., :4] <= floor + 1e-4).mean() > 0.05
