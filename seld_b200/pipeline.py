@@ -158,3 +158,73 @@ def extract_normalized_dataset(wav, sample_rate, mode='foa', n_mels=64, t_out=No
     mean, std = finish_statistics(acc, feat.shape[2], feat.shape[3])
     finalize_(feat, key, t_raw, mean, std)
     return feat, mean, std
+
+
+class HostDatasetExtractor:
+    """End-to-end form with HOST buffers: pinned wav in, pinned normalised features out.
+
+    The reference's `__main__` touches every clip three times on the host (extract, concatenate for mean/std,
+    normalise).  Here clips stream host -> device in chunks on a copy stream, double-buffered against the extract
+    kernel; features stay resident in HBM until the (all-reduced) statistics are known, then are normalised in
+    place and streamed back.  PCIe is the bound of this path, not the kernels.
+    """
+
+    def __init__(self, n_clips, n_samples, sample_rate, mode='foa', n_mels=64, t_out=None, chunk_clips=24,
+                 device=None, **kwargs):
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_clips, self.n_samples, self.sample_rate = int(n_clips), int(n_samples), sample_rate
+        self.mode, self.n_mels, self.kwargs = mode, n_mels, dict(kwargs)
+        self.chunk = max(1, min(int(chunk_clips), self.n_clips))
+        with torch.cuda.device(self.device):
+            self.plan = get_plan(sample_rate, mode=mode, n_mels=n_mels, **self.kwargs)
+            self.t_raw = self.plan.num_frames(n_samples)
+            self.t_out = self.t_raw if t_out is None else int(t_out)
+            self.stage = [torch.empty(self.chunk, 4, n_samples, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self.feat = torch.empty(self.n_clips, self.t_out, n_mels, self.plan.n_out_ch, dtype=torch.float32,
+                                    device=self.device)
+            self.key = torch.empty(self.n_clips, dtype=torch.int32, device=self.device)
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+            self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+            self.stage_free = [torch.cuda.Event() for _ in range(2)]
+        self.h2d_bytes = self.n_clips * 4 * self.n_samples * 4
+        self.d2h_bytes = self.feat.numel() * 4
+
+    def run(self, wav_host, out_host):
+        """wav_host: pinned float32 [n_clips, 4, L]; out_host: pinned float32 [n_clips, t_out, n_mels, C].
+        Returns (mean, std) on the device.  Synchronises before returning (the result is on the host)."""
+        lib = _lib.load()
+        main = torch.cuda.current_stream(self.device)
+        n_ch = self.plan.n_out_ch
+        with torch.cuda.device(self.device):
+            acc = new_accumulator(self.n_mels, n_ch, self.device)
+            for e in self.stage_free:
+                e.record(main)
+            starts = list(range(0, self.n_clips, self.chunk))
+            for i, s in enumerate(starts):
+                n = min(self.chunk, self.n_clips - s)
+                b = i & 1
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(self.stage_free[b])
+                    self.stage[b][:n].copy_(wav_host[s:s + n], non_blocking=True)
+                    self.h2d_done[b].record(self.copy_stream)
+                main.wait_event(self.h2d_done[b])
+                _lib.check(lib.seld_extract(self.plan.handle, _lib.ptr(self.stage[b]), _lib.LAYOUT_PLANAR_CL, n,
+                                            self.n_samples, self.t_out, _lib.ptr(self.feat[s:]), _lib.ptr(self.key[s:]),
+                                            _lib.current_stream_ptr()))
+                self.stage_free[b].record(main)
+            partial_statistics(self.feat, self.key, self.t_raw, acc)
+            allreduce_statistics(acc)
+            mean, std = finish_statistics(acc, self.n_mels, n_ch)
+            # normalise chunk by chunk so the device -> host copies overlap the remaining normalisation
+            done = torch.cuda.Event()
+            for s in starts:
+                n = min(self.chunk, self.n_clips - s)
+                finalize_(self.feat[s:s + n], self.key[s:s + n], self.t_raw, mean, std)
+                done.record(main)
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(done)
+                    out_host[s:s + n].copy_(self.feat[s:s + n], non_blocking=True)
+                done = torch.cuda.Event()
+            self.copy_stream.synchronize()
+            main.synchronize()
+        return mean, std
