@@ -135,7 +135,7 @@ def workload_config(args, clips):
     return {'workload': f'{clips} synthetic 60 s 4-ch 24 kHz {args.mode.upper()} clips per GPU -> '
                         f'[{clips},3000,64,{7 if args.mode == "foa" else 10}] float32: fused extract + per-bin mean/std '
                         f'(all-reduce when N>1) + top_db clamp + normalise (BASELINE.json configs[1]/[3] shape)',
-            'clips_per_gpu': clips, 'mode': args.mode, 'n_fft': 1024, 'win_length': 960, 'hop_length': 480, 'n_mels': 64,
+            'clips_per_gpu': clips, 'mode': args.mode, 'layout': args.layout, 'n_fft': 1024, 'win_length': 960, 'hop_length': 480, 'n_mels': 64,
             'l2': 'inputs (23 MB/clip, 13.8 GB/shard) and outputs (3.2 GB) are far larger than the 126 MB L2; no flush needed',
             'parallelism': f'clip-sharded x{args.gpus}'}
 
@@ -150,8 +150,10 @@ def main():
     ap.add_argument('--clips', type=int, default=600, help='clips per GPU (dev-set shape: 600)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--e2e-clips', type=int, default=None)
-    ap.add_argument('--cpu-clips', type=int, default=16, help='bounded CPU-baseline sample (full-size clips)')
+    ap.add_argument('--cpu-clips', type=int, default=256, help='bounded CPU-baseline sample (full-size clips)')
     ap.add_argument('--ref-clips', type=int, default=8, help='clips per step of --impl reference')
+    ap.add_argument('--layout', default='planar', choices=['planar', 'interleaved'],
+                    help="planar [n,4,L] is the reference's (torchaudio.load) layout")
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
@@ -191,13 +193,16 @@ def main():
     del base
     feat = torch.empty(n, T_OUT, N_MELS, n_ch, dtype=torch.float32, device=dev)
     t_raw = 1 + L // PROD['hop_length']
+    wav_k = wav
+    if args.layout == 'interleaved':
+        wav_k = wav.transpose(1, 2).contiguous()
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
 
     def step(i=None):
         e = ev[i] if i is not None else None
         if e: e[0].record()
-        f, key = pipeline.extract_batch(wav, SR, mode=mode, n_mels=N_MELS, t_out=T_OUT, out=feat, **PROD)
+        f, key = pipeline.extract_batch(wav_k, SR, mode=mode, n_mels=N_MELS, t_out=T_OUT, out=feat, layout=args.layout, **PROD)
         if e: e[1].record()
         acc = pipeline.partial_statistics(f, key, t_raw)
         pipeline.allreduce_statistics(acc)
@@ -252,7 +257,7 @@ def main():
             host_in = torch.empty(ne, 4, L, dtype=torch.float32, pin_memory=True)
             host_out = torch.empty(ne, T_OUT, N_MELS, n_ch, dtype=torch.float32, pin_memory=True)
             host_in.copy_(wav[:ne])
-            del wav, feat
+            del wav, feat, wav_k
             torch.cuda.empty_cache()
             ex = pipeline.HostDatasetExtractor(ne, L, SR, mode=mode, n_mels=N_MELS, t_out=T_OUT, chunk_clips=24, **PROD)
             ex.run(host_in, host_out)                                     # warm-up

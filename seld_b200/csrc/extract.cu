@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "extract_core.cuh"
+#include "mel_pieces.h"
 #include "plan.h"
 
 namespace seld {
@@ -30,14 +31,19 @@ struct ExtractArgs {
     int n_clips;
     long long n_samples;
     int t_raw, t_out, t_tot;
+    int t_lo, t_hi;           // frames [t_lo, t_hi) lie wholly inside the clip (no reflection); the rest are edge frames
     float* out;
     unsigned int* clip_max_key;
     const float* window;
-    const float2* twiddle;
-    const int* seg;
-    const float* w0;
-    const float* w1;
-    int hop, n_mels, n_out_ch;
+    const float2* tw_t;
+    const float2* tw_lin;
+    const float2* w01;
+    const unsigned long long* endmask;
+    const int* piece0;
+    const int* pb;
+    int hop, n_mels;
+    int e_bytes;              // per-warp exchange / piece buffer size
+    int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
     long long n_super;        // super-chunks of warps_per_cta * kFramesPerWarp frames
 };
 
@@ -45,24 +51,29 @@ constexpr int kFramesPerWarp = 8;
 
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 
-template <int R>
-__host__ __device__ constexpr int table_bytes() {
+// CTA-shared tables: lane-contiguous twiddles, mel pieces, and (MIC only) the linear twiddle table
+template <int R, int MODE>
+__host__ __device__ constexpr int table_bytes(int n_mels) {
     using G = Geo<R>;
-    return align16(G::N * 4) + align16(G::N * 8) + 3 * align16(G::F * 4);
+    return align16(G::N * 8) + align16(32 * G::BPT * 8) + align16(32 * 8) + align16(32 * 4) + align16((n_mels + 2) * 4) +
+           (MODE == MODE_MIC ? align16(G::N * 8) : 0);
 }
-template <int R>
-__host__ __device__ constexpr int warp_bytes(int n_mels, int n_out_ch) {
+template <int R, int MODE>
+__host__ __device__ constexpr int warp_bytes(int n_mels, int e_bytes) {
     using G = Geo<R>;
-    return align16(G::E_ELEMS * 8) + 2 * align16(G::N * 8) + align16(n_mels * n_out_ch * 4);
+    return e_bytes + 2 * align16(G::N * 8) + align16(n_mels * (MODE == MODE_FOA ? 7 : 10) * 4);
 }
 
 // register budget follows from the CTA size shared memory allows: 16 warps for n_fft <= 512, 8 for 1024, 4 for 2048
 template <int R>
 __host__ __device__ constexpr int max_warps() { return R <= 16 ? 16 : (R == 32 ? 8 : 4); }
 
-template <int R, int MODE>
+// EDGE = false: interior frames only, loads specialised on LAYOUT (the hot kernel).
+// EDGE = true : the few frames per clip that need reflection, plus the zero padding rows (generic strided loads).
+template <int R, int MODE, int LAYOUT, bool EDGE>
 __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(ExtractArgs a) {
     using G = Geo<R>;
+    constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -70,33 +81,36 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
 
     // ---- CTA-shared tables
     unsigned char* p = smem;
-    float* s_window = reinterpret_cast<float*>(p);  p += align16(G::N * 4);
-    float2* s_twiddle = reinterpret_cast<float2*>(p);  p += align16(G::N * 8);
-    int* s_seg = reinterpret_cast<int*>(p);  p += align16(G::F * 4);
-    float* s_w0 = reinterpret_cast<float*>(p);  p += align16(G::F * 4);
-    float* s_w1 = reinterpret_cast<float*>(p);  p += align16(G::F * 4);
+    float2* s_tw_t = reinterpret_cast<float2*>(p);  p += align16(G::N * 8);
+    float2* s_w01 = reinterpret_cast<float2*>(p);  p += align16(32 * G::BPT * 8);
+    unsigned long long* s_endmask = reinterpret_cast<unsigned long long*>(p);  p += align16(32 * 8);
+    int* s_piece0 = reinterpret_cast<int*>(p);  p += align16(32 * 4);
+    int* s_pb = reinterpret_cast<int*>(p);  p += align16((a.n_mels + 2) * 4);
+    float2* s_tw_lin = nullptr;
+    if constexpr (MODE == MODE_MIC) { s_tw_lin = reinterpret_cast<float2*>(p);  p += align16(G::N * 8); }
     for (int i = threadIdx.x; i < G::N; i += blockDim.x) {
-        s_window[i] = a.window[i];
-        s_twiddle[i] = a.twiddle[i];
+        s_tw_t[i] = a.tw_t[i];
+        if constexpr (MODE == MODE_MIC) s_tw_lin[i] = a.tw_lin[i];
     }
-    for (int i = threadIdx.x; i < G::F; i += blockDim.x) {
-        s_seg[i] = a.seg[i];
-        s_w0[i] = a.w0[i];
-        s_w1[i] = a.w1[i];
-    }
+    for (int i = threadIdx.x; i < 32 * G::BPT; i += blockDim.x) s_w01[i] = a.w01[i];
+    for (int i = threadIdx.x; i < a.n_mels + 2; i += blockDim.x) s_pb[i] = a.pb[i];
+    if (threadIdx.x < 32) { s_endmask[threadIdx.x] = a.endmask[threadIdx.x]; s_piece0[threadIdx.x] = a.piece0[threadIdx.x]; }
     // ---- per-warp regions
-    const int wbytes = warp_bytes<R>(a.n_mels, a.n_out_ch);
+    const int wbytes = warp_bytes<R, MODE>(a.n_mels, a.e_bytes);
     unsigned char* wp = p + size_t(warp) * wbytes;
-    float2* E = reinterpret_cast<float2*>(wp);  wp += align16(G::E_ELEMS * 8);
+    float2* E = reinterpret_cast<float2*>(wp);  wp += a.e_bytes;          // exchange buffer, then mel pieces
     float2* S0 = reinterpret_cast<float2*>(wp);  wp += align16(G::N * 8);
     float2* S1 = reinterpret_cast<float2*>(wp);  wp += align16(G::N * 8);
     float* acc = reinterpret_cast<float*>(wp);
-    const int row_elems = a.n_mels * a.n_out_ch;
-    for (int e = lane; e < row_elems; e += 32) acc[e] = 0.f;
+    const int row_elems = a.n_mels * C;
+    // ---- this lane's window taps stay in registers for the whole kernel
+    float wreg[R];
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2) wreg[n2] = a.window[lane + 32 * n2];
     __syncthreads();
 
-    const Tables tb{s_window, s_twiddle, s_seg, s_w0, s_w1};
-    const long long total_frames = (long long)a.n_clips * a.t_tot;
+    const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_piece0, s_pb};
+    const long long total_frames = (long long)a.n_clips * a.frames_per_clip;
 
     float run_max = -INFINITY;
     int run_clip = -1;
@@ -106,12 +120,17 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
         for (int i = 0; i < kFramesPerWarp; ++i) {
             const long long g = g0 + i;
             if (g >= total_frames) break;
-            const int clip = int(g / a.t_tot);
-            const int t = int(g - (long long)clip * a.t_tot);
+            const int clip = int(g / a.frames_per_clip);
+            const int j = int(g - (long long)clip * a.frames_per_clip);
+            int t;
+            if constexpr (EDGE) t = (j < a.t_lo) ? j : a.t_hi + (j - a.t_lo);
+            else t = a.t_lo + j;
             float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
-            if (t >= a.t_raw) {                       // zero padding rows (reference :142-145)
-                for (int e = lane; e < row_elems; e += 32) row[e] = 0.f;
-                continue;
+            if constexpr (EDGE) {
+                if (t >= a.t_raw) {                   // zero padding rows (reference :142-145)
+                    for (int e = lane; e < row_elems; e += 32) row[e] = 0.f;
+                    continue;
+                }
             }
             if (clip != run_clip) {
                 if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], float_to_key(run_max));
@@ -121,35 +140,39 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
             ClipSrc src;
             src.base = a.wav + (long long)clip * 4 * a.n_samples;
             src.n_samples = a.n_samples;
-            if (a.layout == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
+            if ((EDGE ? a.layout : LAYOUT) == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
             else { src.chan_stride = 1; src.samp_stride = 4; }
             const long long start = (long long)t * a.hop - G::N / 2;
 
-            stage1_forward<R>(src, 0, 1, start, tb, E, lane);
+#pragma unroll 1
+            for (int pr = 0; pr < 2; ++pr) {          // channel pairs (0,1) and (2,3); not unrolled: code size
+                float2 v[R];
+                if constexpr (EDGE) stage1_load_reflect<R>(src, 2 * pr, 2 * pr + 1, start, wreg, v, lane);
+                else stage1_load_interior<R, LAYOUT>(src, 2 * pr, 2 * pr + 1, start, wreg, v, lane);
+                stage1_fft_store<R>(v, tb, E, lane);
+                __syncwarp();
+                stage2_forward<R>(E, pr ? S1 : S0, lane);
+                __syncwarp();
+            }
+            bin_phase<R, MODE>(S0, S1, tb, E, 1e-8f, lane);
             __syncwarp();
-            stage2_forward<R>(E, S0, lane);
-            __syncwarp();
-            stage1_forward<R>(src, 2, 3, start, tb, E, lane);
-            __syncwarp();
-            stage2_forward<R>(E, S1, lane);
-            __syncwarp();
-            bin_phase<R, MODE>(S0, S1, tb, acc, a.n_mels, a.n_out_ch, 1e-8f, lane);
+            float mx = gather_phase<MODE>(E, tb, acc, a.n_mels, lane);
             __syncwarp();
             if constexpr (MODE == MODE_MIC) {
                 gcc_stage1<R, 0>(S0, S1, E, lane);
                 __syncwarp();
-                gcc_stage2<R, 0>(E, tb, acc, a.n_mels, a.n_out_ch, lane);
+                gcc_stage2<R, 0>(E, tb, acc, a.n_mels, lane);
                 __syncwarp();
                 gcc_stage1<R, 1>(S0, S1, E, lane);
                 __syncwarp();
-                gcc_stage2<R, 1>(E, tb, acc, a.n_mels, a.n_out_ch, lane);
+                gcc_stage2<R, 1>(E, tb, acc, a.n_mels, lane);
                 __syncwarp();
                 gcc_stage1<R, 2>(S0, S1, E, lane);
                 __syncwarp();
-                gcc_stage2<R, 2>(E, tb, acc, a.n_mels, a.n_out_ch, lane);
+                gcc_stage2<R, 2>(E, tb, acc, a.n_mels, lane);
                 __syncwarp();
             }
-            float mx = finish_row(acc, a.n_mels, a.n_out_ch, row, lane);
+            if (row != nullptr) store_row(acc, row_elems, row, lane);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             run_max = fmaxf(run_max, mx);
@@ -164,31 +187,52 @@ __global__ void clip_max_decode_kernel(const unsigned int* keys, int n, float* o
     if (i < n) out[i] = key_to_float(keys[i]);
 }
 
-template <int R>
-static int launch_extract(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
-    const int threads = plan->warps_per_cta * 32;
-    if (plan->mode == SELD_MODE_FOA) {
-        SELD_CUDA_TRY(cudaFuncSetAttribute(extract_kernel<R, MODE_FOA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           plan->extract_smem_bytes));
-        extract_kernel<R, MODE_FOA><<<plan->grid, threads, plan->extract_smem_bytes, stream>>>(a);
-    } else {
-        SELD_CUDA_TRY(cudaFuncSetAttribute(extract_kernel<R, MODE_MIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           plan->extract_smem_bytes));
-        extract_kernel<R, MODE_MIC><<<plan->grid, threads, plan->extract_smem_bytes, stream>>>(a);
-    }
+template <int R, int MODE, int LAYOUT, bool EDGE>
+static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream) {
+    a.frames_per_clip = EDGE ? a.t_lo + (a.t_tot - a.t_hi) : a.t_hi - a.t_lo;
+    if (a.frames_per_clip <= 0) return SELD_OK;
+    const long long per_super = (long long)plan->warps_per_cta * kFramesPerWarp;
+    a.n_super = ((long long)a.n_clips * a.frames_per_clip + per_super - 1) / per_super;
+    long long grid = a.n_super < plan->grid ? a.n_super : plan->grid;
+    SELD_CUDA_TRY(cudaFuncSetAttribute(extract_kernel<R, MODE, LAYOUT, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       plan->extract_smem_bytes));
+    extract_kernel<R, MODE, LAYOUT, EDGE><<<(int)grid, plan->warps_per_cta * 32, plan->extract_smem_bytes, stream>>>(a);
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;
 }
 
+template <int R, int MODE>
+static int launch_mode(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
+    int rc = (a.layout == SELD_LAYOUT_PLANAR_CL) ? launch_one<R, MODE, LAYOUT_PLANAR_CL, false>(plan, a, stream)
+                                                 : launch_one<R, MODE, LAYOUT_INTERLEAVED_LC, false>(plan, a, stream);
+    if (rc != SELD_OK) return rc;
+    return launch_one<R, MODE, LAYOUT_PLANAR_CL, true>(plan, a, stream);      // edge frames: layout taken from a.layout
+}
+
 template <int R>
-static void plan_geometry(seld_plan* plan) {
-    const int tb = table_bytes<R>();
-    const int wb = warp_bytes<R>(plan->n_mels, plan->n_out_ch);
+static int launch_extract(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
+    return plan->mode == SELD_MODE_FOA ? launch_mode<R, MODE_FOA>(plan, a, stream) : launch_mode<R, MODE_MIC>(plan, a, stream);
+}
+
+template <int R, int MODE>
+static void plan_geometry_mode(seld_plan* plan) {
+    using G = Geo<R>;
+    const int pstride = (MODE == MODE_FOA) ? 64 : 32;
+    int e_bytes = align16(G::E_ELEMS * 8);
+    if (plan->n_pieces * pstride > e_bytes) e_bytes = align16(plan->n_pieces * pstride);
+    plan->e_bytes = e_bytes;
+    const int tb = table_bytes<R, MODE>(plan->n_mels);
+    const int wb = warp_bytes<R, MODE>(plan->n_mels, e_bytes);
     int warps = (plan->max_smem_optin - tb) / wb;
     if (warps > max_warps<R>()) warps = max_warps<R>();
     plan->warps_per_cta = warps;
     plan->extract_smem_bytes = tb + warps * wb;
     plan->grid = plan->num_sms;
+}
+template <int R>
+static void plan_geometry(seld_plan* plan) {
+    if (plan->mode == SELD_MODE_FOA) plan_geometry_mode<R, MODE_FOA>(plan);
+    else plan_geometry_mode<R, MODE_MIC>(plan);
 }
 
 }  // namespace seld
@@ -255,29 +299,15 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
     cudaDeviceGetAttribute(&plan->num_sms, cudaDevAttrMultiProcessorCount, plan->device);
     cudaDeviceGetAttribute(&plan->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan->device);
 
-    // sparse form of the mel bank: <= 2 adjacent non-zeros per row
-    const int F = plan->n_bins;
-    std::vector<int> seg(F, -1);
-    std::vector<float> w0(F, 0.f), w1(F, 0.f);
-    for (int k = 0; k < F; ++k) {
-        int first = -1, count = 0, last = -1;
-        for (int m = 0; m < n_mels; ++m) {
-            if (mel_fb_host[(size_t)k * n_mels + m] != 0.f) {
-                if (first < 0) first = m;
-                last = m;
-                ++count;
-            }
-        }
-        if (count == 0) continue;
-        if (count > 2 || last - first > 1) {
-            delete plan;
-            set_error("mel filterbank row has more than two / non-adjacent non-zeros");
-            return SELD_EUNSUPPORTED;
-        }
-        seg[k] = first;
-        w0[k] = mel_fb_host[(size_t)k * n_mels + first];
-        if (count == 2) w1[k] = mel_fb_host[(size_t)k * n_mels + last];
+    // piece form of the mel bank (<= 2 adjacent non-zeros per row, increasing centres)
+    MelPieces mp;
+    const std::string perr = build_mel_pieces(mel_fb_host, plan->n_bins, n_mels, mp);
+    if (!perr.empty()) {
+        delete plan;
+        set_error(perr);
+        return SELD_EUNSUPPORTED;
     }
+    plan->n_pieces = mp.n_pieces;
     std::vector<float> tw(2 * (size_t)n_fft);
     for (int j = 0; j < n_fft; ++j) {
         const double ang = -2.0 * 3.14159265358979323846264338327950288 * double(j) / double(n_fft);
@@ -292,9 +322,18 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
     };
     up((void**)&plan->window, window_host, sizeof(float) * n_fft);
     up((void**)&plan->twiddle, tw.data(), sizeof(float) * 2 * n_fft);
-    up((void**)&plan->seg, seg.data(), sizeof(int) * F);
-    up((void**)&plan->w0, w0.data(), sizeof(float) * F);
-    up((void**)&plan->w1, w1.data(), sizeof(float) * F);
+    std::vector<float> twt(2 * (size_t)n_fft);          // tw_t[k2*32 + lane] = W^(lane*k2): lane-contiguous, conflict-free
+    for (int k2 = 0; k2 < n_fft / 32; ++k2)
+        for (int l = 0; l < 32; ++l) {
+            const int j = (l * k2) % n_fft;
+            twt[2 * (k2 * 32 + l)] = tw[2 * j];
+            twt[2 * (k2 * 32 + l) + 1] = tw[2 * j + 1];
+        }
+    up((void**)&plan->tw_t, twt.data(), sizeof(float) * 2 * n_fft);
+    up((void**)&plan->w01, mp.w01.data(), sizeof(float) * mp.w01.size());
+    up((void**)&plan->endmask, mp.endmask.data(), sizeof(unsigned long long) * 32);
+    up((void**)&plan->piece0, mp.piece0.data(), sizeof(int) * 32);
+    up((void**)&plan->pb, mp.pb.data(), sizeof(int) * mp.pb.size());
     if (e != cudaSuccess) {
         seld_plan_destroy(plan);
         return cuda_fail(e, "plan table upload");
@@ -319,9 +358,11 @@ int seld_plan_destroy(seld_plan_t plan) {
     if (!plan) return SELD_OK;
     cudaFree(plan->window);
     cudaFree(plan->twiddle);
-    cudaFree(plan->seg);
-    cudaFree(plan->w0);
-    cudaFree(plan->w1);
+    cudaFree(plan->tw_t);
+    cudaFree(plan->w01);
+    cudaFree(plan->endmask);
+    cudaFree(plan->piece0);
+    cudaFree(plan->pb);
     delete plan;
     return SELD_OK;
 }
@@ -355,15 +396,25 @@ int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips
     a.out = feat_raw_dev;
     a.clip_max_key = clip_max_key_dev;
     a.window = plan->window;
-    a.twiddle = reinterpret_cast<const float2*>(plan->twiddle);
-    a.seg = plan->seg;
-    a.w0 = plan->w0;
-    a.w1 = plan->w1;
+    a.tw_t = reinterpret_cast<const float2*>(plan->tw_t);
+    a.tw_lin = reinterpret_cast<const float2*>(plan->twiddle);
+    a.w01 = reinterpret_cast<const float2*>(plan->w01);
+    a.endmask = plan->endmask;
+    a.piece0 = plan->piece0;
+    a.pb = plan->pb;
+    a.e_bytes = plan->e_bytes;
+    // frames [t_lo, t_hi) need no reflection: t*hop - n_fft/2 >= 0 and t*hop + n_fft/2 <= n_samples
+    {
+        const long long half = plan->n_fft / 2;
+        long long lo = (half + plan->hop - 1) / plan->hop;
+        long long hi = (n_samples >= half) ? (n_samples - half) / plan->hop + 1 : 0;
+        if (hi > a.t_raw) hi = a.t_raw;
+        if (lo > hi) lo = hi;
+        a.t_lo = int(lo);
+        a.t_hi = int(hi);
+    }
     a.hop = plan->hop;
     a.n_mels = plan->n_mels;
-    a.n_out_ch = plan->n_out_ch;
-    const long long per_super = (long long)plan->warps_per_cta * kFramesPerWarp;
-    a.n_super = ((long long)n_clips * a.t_tot + per_super - 1) / per_super;
     SELD_CUDA_TRY(cudaMemsetAsync(clip_max_key_dev, 0, sizeof(uint32_t) * n_clips, st));
     switch (plan->n_fft) {
         case 256: return launch_extract<8>(plan, a, st);

@@ -10,7 +10,9 @@
 //
 // Algorithm (N = n_fft = 32*R, lane = threadIdx & 31):
 //   stage 1  lane holds x[lane + 32*n2], n2 < R, of TWO real channels packed as re/im; R-point
-//            DIF FFT in registers; twiddle W_N^(lane*k2); transposed through the warp's exchange buffer.
+//            DIF FFT in registers (packed f32x2 butterflies: the kernel is issue-bound and FADD2/FFMA2
+//            do two FP32 lanes per issue slot); twiddle W_N^(lane*k2) from a lane-contiguous table;
+//            transposed through the warp's exchange buffer with 128-bit stores.
 //   stage 2  lane k2 runs a 32-point FFT down its column -> Z[R*k1 + k2] written to the spectrum buffer.
 //   bins     lane owns a contiguous run of bins k, splits Z[k], Z[N-k] into the two real channels'
 //            spectra, forms power / intensity vectors (or per-channel unit phasors), and reduces them
@@ -29,11 +31,15 @@ enum { MODE_FOA = 0, MODE_MIC = 1 };
 enum { LAYOUT_PLANAR_CL = 0, LAYOUT_INTERLEAVED_LC = 1 };
 
 struct Tables {             // CTA-shared constant tables (shared memory on the device)
-    const float* window;    // [N]   periodic Hann(win_length) zero-padded centred to N
-    const float2* twiddle;  // [N]   exp(-2 pi i j / N)
-    const int* seg;         // [F]   first mel filter fed by bin k (-1: none)
-    const float* w0;        // [F]   weight into filter seg[k]
-    const float* w1;        // [F]   weight into filter seg[k] + 1
+    const float* window;    // [N]      periodic Hann(win_length) zero-padded centred to N
+    const float2* tw_t;     // [R][32]  tw_t[k2*32 + lane] = exp(-2 pi i lane*k2 / N)   (lane-contiguous)
+    const float2* tw_lin;   // [N]      exp(-2 pi i j / N)  (generic GCC lags only; may be null otherwise)
+    // sparse mel bank in "piece" form (built by seld_plan_create): lane l owns bins [l*BPT, (l+1)*BPT); a piece is a
+    // maximal run of one lane's bins that feed the same pair of adjacent filters (seg, seg+1)
+    const float2* w01;          // [32*BPT] 0.25 * (weight into filter seg, weight into filter seg+1); 0 past bin F-1
+    const unsigned long long* endmask;  // [32] bit i set: bin l*BPT + i is the last bin of a piece
+    const int* piece0;          // [32]     index of lane l's first piece
+    const int* pb;              // [n_mels + 2] pieces with seg == m are [pb[m+1], pb[m+2])
 };
 
 struct ClipSrc {            // one clip's samples: channel c, sample i -> base[c * chan_stride + i * samp_stride]
@@ -47,7 +53,7 @@ template <int R>
 struct Geo {
     static constexpr int N = 32 * R;
     static constexpr int F = N / 2 + 1;
-    static constexpr int EP = R + 1;                 // padded row length of the exchange buffer
+    static constexpr int EP = R + 2;                 // padded row of the exchange buffer: 128-bit stores conflict-free
     static constexpr int E_ELEMS = 32 * EP;          // float2 elements
     static constexpr int COLS = (R + 31) / 32;       // stage-2 columns per lane
     static constexpr int BPT = (F + 31) / 32;        // bins per lane in the bin phase
@@ -60,35 +66,152 @@ struct Geo {
 #define SELD_SMEM_ADD(ptr, v) (*(ptr) += (v))
 #endif
 
+// ---------------------------------------------------------------- packed FP32x2 arithmetic (FADD2 / FMUL2 / FFMA2)
+SELD_HD float2 padd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    float2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return r;
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+SELD_HD float2 psub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    float2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return r;
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+SELD_HD float2 pmul(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    float2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return r;
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+SELD_HD float2 pfma(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+    float2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return r;
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+// d * (c + i s) in two packed instructions: d*(c,c) then swap(d)*(-s,s) + .
+SELD_HD float2 pcmul(float2 d, float c, float s) {
+    return pfma(make_float2(d.y, d.x), make_float2(-s, s), pmul(d, make_float2(c, c)));
+}
+
+template <int J, int N>
+SELD_HD float2 pmul_tw(float2 d) {   // d * W_N^J, compile-time twiddle
+    if constexpr (J == 0) {
+        return d;
+    } else if constexpr (4 * J == N) {
+        return make_float2(d.y, -d.x);
+    } else {
+        return pcmul(d, Tw<J, N>::re, Tw<J, N>::im);
+    }
+}
+
+template <int N, int J>
+struct PButterflies {
+    static SELD_HD void run(float2* v) {
+        const float2 a = v[J], b = v[J + N / 2];
+        v[J] = padd(a, b);
+        v[J + N / 2] = pmul_tw<J, N>(psub(a, b));
+        if constexpr (J + 1 < N / 2) PButterflies<N, J + 1>::run(v);
+    }
+};
+
+// Forward DFT of v[0..N) in registers, result bit-reversed: v[p] = X[bitrev(p)].
+template <int N>
+SELD_HD void pfft_dif(float2* v) {
+    if constexpr (N >= 2) {
+        PButterflies<N, 0>::run(v);
+        pfft_dif<N / 2>(v);
+        pfft_dif<N / 2>(v + N / 2);
+    }
+}
+
 // ---------------------------------------------------------------- stage 1: load, window, R-point FFT, twiddle
+// wreg[n2] = window[lane + 32*n2] is held in registers by the caller for the whole kernel.
+// Interior frames (whole frame inside the clip, no reflection): one 64-bit load per tap when the two channels
+// of the pair are adjacent in memory (interleaved layout, ch_b == ch_a + 1, ch_a even), else two 32-bit loads.
+template <int R, int LAYOUT>
+SELD_HD void stage1_load_interior(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, const float* wreg,
+                                  float2* v, int lane) {
+    if constexpr (LAYOUT == LAYOUT_INTERLEAVED_LC) {
+        const float2* p = reinterpret_cast<const float2*>(src.base + (frame_start + lane) * 4 + ch_a);
+#pragma unroll
+        for (int n2 = 0; n2 < R; ++n2) {
+            const float2 s = p[64 * n2];
+            v[n2] = make_float2(wreg[n2] * s.x, wreg[n2] * s.y);
+        }
+    } else {
+        const float* pa = src.base + ch_a * src.chan_stride + frame_start + lane;       // planar: samp_stride == 1
+        const float* pb = src.base + ch_b * src.chan_stride + frame_start + lane;
+#pragma unroll
+        for (int n2 = 0; n2 < R; ++n2) v[n2] = make_float2(wreg[n2] * pa[32 * n2], wreg[n2] * pb[32 * n2]);
+    }
+}
+
+// Edge frames: reflect without edge repeat (torch.stft center=True, pad_mode='reflect').
 template <int R>
-SELD_HD void stage1_forward(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, const Tables& tb,
-                            float2* E, int lane) {
-    using G = Geo<R>;
-    float2 v[R];
+SELD_HD void stage1_load_reflect(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, const float* wreg,
+                                 float2* v, int lane) {
     const float* xa = src.base + ch_a * src.chan_stride;
     const float* xb = src.base + ch_b * src.chan_stride;
     const long long L = src.n_samples;
 #pragma unroll
     for (int n2 = 0; n2 < R; ++n2) {
-        const int n = lane + 32 * n2;
-        const float w = tb.window[n];
-        long long i = frame_start + n;
-        if (i < 0) i = -i;                       // reflect, no edge repeat (torch.stft center=True)
+        long long i = frame_start + lane + 32 * n2;
+        if (i < 0) i = -i;
         if (i >= L) i = 2 * (L - 1) - i;
         float a = 0.f, b = 0.f;
-        if (w != 0.f) {
+        if (wreg[n2] != 0.f) {
             a = xa[i * src.samp_stride];
             b = xb[i * src.samp_stride];
         }
-        v[n2] = make_float2(w * a, w * b);
+        v[n2] = make_float2(wreg[n2] * a, wreg[n2] * b);
     }
-    fft_dif<R>(v);
+}
+
+template <int R>
+SELD_HD void stage1_fft_store(float2* v, const Tables& tb, float2* E, int lane) {
+    using G = Geo<R>;
+    pfft_dif<R>(v);
+    // twiddle W_N^(lane*k2), then two neighbouring k2 per 128-bit store
+    float4* E4 = reinterpret_cast<float4*>(E + lane * G::EP);
 #pragma unroll
-    for (int p = 0; p < R; ++p) {
-        const int k2 = bitrev(p, G::LOG2R);
-        E[lane * G::EP + k2] = cmul(v[p], tb.twiddle[lane * k2]);
+    for (int j = 0; j < R / 2; ++j) {
+        const int p0 = bitrev(2 * j, G::LOG2R), p1 = bitrev(2 * j + 1, G::LOG2R);
+        const float2 t0 = tb.tw_t[(2 * j) * 32 + lane], t1 = tb.tw_t[(2 * j + 1) * 32 + lane];
+        const float2 a = pcmul(v[p0], t0.x, t0.y), b = pcmul(v[p1], t1.x, t1.y);
+        float4 q; q.x = a.x; q.y = a.y; q.z = b.x; q.w = b.y;
+        E4[j] = q;
     }
+}
+
+template <int R, int LAYOUT>
+SELD_HD void stage1_forward(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, const float* wreg,
+                            const Tables& tb, float2* E, int lane) {
+    float2 v[R];
+    if (frame_start >= 0 && frame_start + 32 * R <= src.n_samples)      // warp-uniform
+        stage1_load_interior<R, LAYOUT>(src, ch_a, ch_b, frame_start, wreg, v, lane);
+    else
+        stage1_load_reflect<R>(src, ch_a, ch_b, frame_start, wreg, v, lane);
+    stage1_fft_store<R>(v, tb, E, lane);
 }
 
 // ---------------------------------------------------------------- stage 2: 32-point FFT per column
@@ -102,17 +225,11 @@ SELD_HD void stage2_forward(const float2* E, float2* S, int lane) {
             float2 u[32];
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) u[n1] = E[n1 * G::EP + k2];
-            fft_dif<32>(u);
+            pfft_dif<32>(u);
 #pragma unroll
             for (int p = 0; p < 32; ++p) S[R * bitrev(p, 5) + k2] = u[p];
         }
     }
-}
-
-// split packed spectrum Z = FFT(a + i b) at bin k (zn = Z[N-k]) into A[k], B[k]
-SELD_HD void unpack2(float2 z, float2 zn, float2& A, float2& B) {
-    A = make_float2(0.5f * (z.x + zn.x), 0.5f * (z.y - zn.y));
-    B = make_float2(0.5f * (z.y + zn.y), 0.5f * (zn.x - z.x));
 }
 
 SELD_HD float2 unit_phasor(float2 a) {   // a / |a|, (0,0) for a == 0; scaled so |a|^2 neither under- nor overflows
@@ -128,75 +245,133 @@ SELD_HD float2 unit_phasor(float2 a) {   // a / |a|, (0,0) for a == 0; scaled so
     return make_float2(x * r, y * r);
 }
 
+SELD_HD float fast_rsqrt(float s) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(s);
+#else
+    return 1.0f / sqrtf(s);
+#endif
+}
+
 // ---------------------------------------------------------------- bin phase
 // NV = 7 (FOA: 4 powers + 3 normalised intensity components) or 4 (MIC: powers; unit phasors are
-// written back in place of the packed spectra for the GCC phase).
+// written back in place of the packed spectra for the GCC phase).  With Z = FFT(a + i b):
+// 2 A[k] = Z[k] + conj(Z[N-k]), 2 B[k] = -i (Z[k] - conj(Z[N-k])); the factor 2 is carried: powers come out
+// 4x (the mel weights are pre-scaled by the exact constant 1/4) and the intensity vector, scale-free apart from
+// eps, is produced 4x as well.  Each lane walks its BPT contiguous bins in straight-line code, accumulating
+// (into filter seg, into filter seg+1) as one packed FFMA2 per channel, and stores the pair sums at the end of every
+// piece: P[piece][c] = (sum w0 val_c, sum w1 val_c).  No atomics, fixed order => bit-reproducible.
 template <int R, int MODE>
-SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float* acc, int n_mels, int n_out_ch,
-                       float eps, int lane) {
+SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, float eps, int lane) {
     using G = Geo<R>;
     constexpr int N = G::N;
     constexpr int NV = (MODE == MODE_FOA) ? 7 : 4;
+    constexpr int PSTRIDE = (MODE == MODE_FOA) ? 8 : 4;         // float2 per piece record (64 B / 32 B)
     const int kbeg = lane * G::BPT;
-    const int kend = (kbeg + G::BPT < G::F) ? kbeg + G::BPT : G::F;
-    int cur = -1;
-    float a0[NV], a1[NV];
+    const unsigned long long endmask = tb.endmask[lane];
+    int piece = tb.piece0[lane];
+    float2 acc2[NV];
 #pragma unroll
-    for (int c = 0; c < NV; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
+    for (int c = 0; c < NV; ++c) acc2[c] = make_float2(0.f, 0.f);
+    const float inv_eps = 1.0f / eps;
 
-    for (int k = kbeg; k < kend; ++k) {
-        const int kn = (N - k) & (N - 1);
-        float2 ch[4];
-        unpack2(S0[k], S0[kn], ch[0], ch[1]);
-        unpack2(S1[k], S1[kn], ch[2], ch[3]);
-        float val[NV];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) val[c] = ch[c].x * ch[c].x + ch[c].y * ch[c].y;
-        if constexpr (MODE == MODE_FOA) {
-            // W = ch0, Y = ch1, Z = ch2, X = ch3; I = Re(conj(W) * {X, Y, Z})
-            float ix = ch[0].x * ch[3].x + ch[0].y * ch[3].y;
-            float iy = ch[0].x * ch[1].x + ch[0].y * ch[1].y;
-            float iz = ch[0].x * ch[2].x + ch[0].y * ch[2].y;
-            float nrm = fmaxf(sqrtf(ix * ix + iy * iy + iz * iz), eps);
-            val[4] = ix / nrm;
-            val[5] = iy / nrm;
-            val[6] = iz / nrm;
-        } else {
-            float2 u0 = unit_phasor(ch[0]), u1 = unit_phasor(ch[1]);
-            float2 u2 = unit_phasor(ch[2]), u3 = unit_phasor(ch[3]);
-            if (k == 0 || k == N / 2) {          // real bins: both channels of a pair share one slot
-                S0[k] = make_float2(u0.x, u1.x);
-                S1[k] = make_float2(u2.x, u3.x);
+    for (int i = 0; i < G::BPT; ++i) {
+        const int k = kbeg + i;
+        if (k < G::F) {
+            const int kn = (N - k) & (N - 1);
+            const float2 z0 = S0[k], z0n = S0[kn], z1 = S1[k], z1n = S1[kn];
+            float2 ch[4];                                  // twice the channel spectra
+            ch[0] = make_float2(z0.x + z0n.x, z0.y - z0n.y);
+            ch[1] = make_float2(z0.y + z0n.y, z0n.x - z0.x);
+            ch[2] = make_float2(z1.x + z1n.x, z1.y - z1n.y);
+            ch[3] = make_float2(z1.y + z1n.y, z1n.x - z1.x);
+            float val[NV];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) val[c] = fmaf(ch[c].x, ch[c].x, ch[c].y * ch[c].y);     // 4 |X_c|^2
+            if constexpr (MODE == MODE_FOA) {
+                // W = ch0, Y = ch1, Z = ch2, X = ch3; I = Re(conj(W) * {X, Y, Z})  (here 4 I)
+                const float ix = fmaf(ch[0].x, ch[3].x, ch[0].y * ch[3].y);
+                const float iy = fmaf(ch[0].x, ch[1].x, ch[0].y * ch[1].y);
+                const float iz = fmaf(ch[0].x, ch[2].x, ch[0].y * ch[2].y);
+                // 4 / max(|4 I|, 4 eps) = min(4 rsqrt(|4 I|^2), 1/eps); rsqrt(0) = inf -> 1/eps, as maximum(norm, eps)
+                const float inv4 = fminf(4.0f * fast_rsqrt(fmaf(ix, ix, fmaf(iy, iy, iz * iz))), inv_eps);
+                val[4] = ix * inv4;
+                val[5] = iy * inv4;
+                val[6] = iz * inv4;
             } else {
-                S0[k] = u0; S0[kn] = u1;
-                S1[k] = u2; S1[kn] = u3;
-            }
-        }
-        const int s = tb.seg[k];
-        if (s < 0) continue;
-        if (s != cur) {
-            if (cur >= 0) {
-#pragma unroll
-                for (int c = 0; c < NV; ++c) {
-                    SELD_SMEM_ADD(&acc[cur * n_out_ch + c], a0[c]);
-                    if (cur + 1 < n_mels) SELD_SMEM_ADD(&acc[(cur + 1) * n_out_ch + c], a1[c]);
+                const float2 u0 = unit_phasor(ch[0]), u1 = unit_phasor(ch[1]);
+                const float2 u2 = unit_phasor(ch[2]), u3 = unit_phasor(ch[3]);
+                if (k == 0 || k == N / 2) {          // real bins: both channels of a pair share one slot
+                    S0[k] = make_float2(u0.x, u1.x);
+                    S1[k] = make_float2(u2.x, u3.x);
+                } else {
+                    S0[k] = u0; S0[kn] = u1;
+                    S1[k] = u2; S1[kn] = u3;
                 }
             }
-            cur = s;
+            const float2 w = tb.w01[k];
 #pragma unroll
-            for (int c = 0; c < NV; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
+            for (int c = 0; c < NV; ++c) acc2[c] = pfma(make_float2(val[c], val[c]), w, acc2[c]);
         }
-        const float w0 = tb.w0[k], w1 = tb.w1[k];
+        if ((endmask >> i) & 1ull) {
+            float4* dst = reinterpret_cast<float4*>(P + piece * PSTRIDE);
 #pragma unroll
-        for (int c = 0; c < NV; ++c) { a0[c] += w0 * val[c]; a1[c] += w1 * val[c]; }
-    }
-    if (cur >= 0) {
+            for (int c = 0; c + 1 < NV; c += 2) {
+                float4 q; q.x = acc2[c].x; q.y = acc2[c].y; q.z = acc2[c + 1].x; q.w = acc2[c + 1].y;
+                dst[c / 2] = q;
+            }
+            if constexpr (NV & 1) {
+                float4 q; q.x = acc2[NV - 1].x; q.y = acc2[NV - 1].y; q.z = 0.f; q.w = 0.f;
+                dst[NV / 2] = q;
+            }
+            ++piece;
 #pragma unroll
-        for (int c = 0; c < NV; ++c) {
-            SELD_SMEM_ADD(&acc[cur * n_out_ch + c], a0[c]);
-            if (cur + 1 < n_mels) SELD_SMEM_ADD(&acc[(cur + 1) * n_out_ch + c], a1[c]);
+            for (int c = 0; c < NV; ++c) acc2[c] = make_float2(0.f, 0.f);
         }
     }
+}
+
+SELD_HD float fast_db(float x) {            // 10 log10(x), x > 0
+#if defined(__CUDA_ARCH__)
+    return 3.0102999566398120f * __log2f(x);     // MUFU.LG2: <= 2 ulp of log2 => <= 2.3e-5 dB at -100 dB, ~6e-6 dB typical
+#else
+    return 3.0102999566398120f * log2f(x);
+#endif
+}
+
+// ---------------------------------------------------------------- gather: pieces -> mel rows
+// Lane l owns filters m = l, l + 32, ...: mel[m][c] = sum_{pieces of seg m} P.x + sum_{pieces of seg m-1} P.y, in piece
+// order.  Log-mel channels get 10 log10(max(., 1e-10)) here; returns the lane's maximum dB.
+template <int MODE>
+SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_mels, int lane) {
+    constexpr int NV = (MODE == MODE_FOA) ? 7 : 4;
+    constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
+    constexpr int PSTRIDE = (MODE == MODE_FOA) ? 8 : 4;
+    float mx = -INFINITY;
+    for (int m = lane; m < n_mels; m += 32) {
+        const int p0 = tb.pb[m], p1 = tb.pb[m + 1], p2 = tb.pb[m + 2];
+        float sum[NV];
+#pragma unroll
+        for (int c = 0; c < NV; ++c) sum[c] = 0.f;
+        for (int p = p0; p < p1; ++p) {                // falling slopes of the segment below
+#pragma unroll
+            for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].y;
+        }
+        for (int p = p1; p < p2; ++p) {                // rising slopes of this filter's own segment
+#pragma unroll
+            for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].x;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float v = fast_db(fmaxf(sum[c], 1e-10f));
+            mx = fmaxf(mx, v);
+            acc[m * C + c] = v;
+        }
+#pragma unroll
+        for (int c = 4; c < NV; ++c) acc[m * C + c] = sum[c];
+    }
+    return mx;
 }
 
 // ---------------------------------------------------------------- GCC-PHAT, packed inverse transform q
@@ -235,16 +410,46 @@ SELD_HD void gcc_stage1(const float2* S0, const float2* S1, float2* E, int lane)
         // conj(Pa + i Pb): the forward FFT of the conjugate is the conjugate of the inverse FFT
         v[n2] = make_float2(pa.x - pb.y, -(pa.y + pb.x));
     }
-    fft_dif<R>(v);
+    pfft_dif<R>(v);
 #pragma unroll
     for (int p = 0; p < R; ++p) E[lane * G::EP + bitrev(p, G::LOG2R)] = v[p];
 }
 
+// W_32^-b as compile-time constants for the fast GCC stage 2
+template <int B>
+SELD_HD float2 mul_conj_w32(float2 t) { return pcmul(t, Tw<B, 32>::re, -Tw<B, 32>::im); }
+
+template <int B>
+struct GccAccum {    // out0 += u[b] W^(b r);  out1 += u[b] W^(b r) W_32^-b
+    static SELD_HD void run(const float2* u, const float2* twcol, float2& o0, float2& o1) {
+        const float2 w = twcol[B * 32];
+        const float2 t = pcmul(u[B], w.x, w.y);
+        o0 = padd(o0, t);
+        o1 = padd(o1, mul_conj_w32<B>(t));
+        if constexpr (B + 1 < 32) GccAccum<B + 1>::run(u, twcol, o0, o1);
+    }
+};
+
 template <int R, int Q>
-SELD_HD void gcc_stage2(const float2* E, const Tables& tb, float* acc, int n_mels, int n_out_ch, int lane) {
+SELD_HD void gcc_stage2(const float2* E, const Tables& tb, float* acc, int n_mels, int lane) {
     using G = Geo<R>;
     constexpr int N = G::N;
+    constexpr int C = 10;
     const float inv_n = 1.0f / float(N);
+    if (R == 32 && n_mels == 64) {   // (dead code for R != 32 is removed: the condition is a constant there)
+        // lags 0..31 are n = r, lags -32..-1 are n = N - 32 + r: W^(b n) = W^(b r) resp. W^(b r) W_32^-b, and
+        // W^(b r) = tw_t[b][r] is lane-contiguous
+        float2 u[32];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) u[b] = E[b * G::EP + lane];
+        float2 o0 = make_float2(0.f, 0.f), o1 = make_float2(0.f, 0.f);
+        GccAccum<0>::run(u, tb.tw_t + lane, o0, o1);
+        acc[(32 + lane) * C + 4 + 2 * Q] = o0.x * inv_n;
+        acc[(32 + lane) * C + 4 + 2 * Q + 1] = -o0.y * inv_n;
+        acc[lane * C + 4 + 2 * Q] = o1.x * inv_n;
+        acc[lane * C + 4 + 2 * Q + 1] = -o1.y * inv_n;
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < G::COLS; ++c) {
         const int r = lane + 32 * c;
@@ -260,34 +465,21 @@ SELD_HD void gcc_stage2(const float2* E, const Tables& tb, float* acc, int n_mel
                 float sx = 0.f, sy = 0.f;
 #pragma unroll
                 for (int b = 0; b < 32; ++b) {
-                    const float2 t = tb.twiddle[(b * n) & (N - 1)];
+                    const float2 t = tb.tw_lin[(b * n) & (N - 1)];
                     sx += u[b].x * t.x - u[b].y * t.y;
                     sy += u[b].x * t.y + u[b].y * t.x;
                 }
-                acc[j * n_out_ch + 4 + 2 * Q] = sx * inv_n;          // Re conj(sum)
-                acc[j * n_out_ch + 4 + 2 * Q + 1] = -sy * inv_n;     // Im conj(sum)
+                acc[j * C + 4 + 2 * Q] = sx * inv_n;          // Re conj(sum)
+                acc[j * C + 4 + 2 * Q + 1] = -sy * inv_n;     // Im conj(sum)
             }
         }
     }
 }
 
 // ---------------------------------------------------------------- finish one frame row
-// acc[m * C + c]: channels < 4 are mel power -> 10 log10(max(., amin)); the rest pass through.
-// Returns this lane's maximum dB value (-inf if it owns no log-mel element).
-SELD_HD float finish_row(float* acc, int n_mels, int n_out_ch, float* out_row /* nullable */, int lane) {
-    float mx = -INFINITY;
-    const int n = n_mels * n_out_ch;
-    for (int e = lane; e < n; e += 32) {
-        const int c = e % n_out_ch;
-        float v = acc[e];
-        if (c < 4) {
-            v = 10.0f * log10f(fmaxf(v, 1e-10f));
-            mx = fmaxf(mx, v);
-        }
-        if (out_row) out_row[e] = v;
-        acc[e] = 0.f;
-    }
-    return mx;
+// Coalesced copy of the staged row acc[m * C + c] to global memory.
+SELD_HD void store_row(const float* acc, int row_elems, float* out_row, int lane) {
+    for (int e = lane; e < row_elems; e += 32) out_row[e] = acc[e];
 }
 
 }  // namespace seld

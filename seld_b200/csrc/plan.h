@@ -17,10 +17,14 @@ struct seld_plan {
     int max_smem_optin;
     // device tables
     float* window;   // [n_fft]
-    float* twiddle;  // [n_fft][2]
-    int* seg;        // [n_bins]
-    float* w0;       // [n_bins]
-    float* w1;       // [n_bins]
+    float* twiddle;  // [n_fft][2]  exp(-2 pi i j / n_fft)
+    float* tw_t;     // [n_fft/32][32][2]  tw_t[k2][lane] = exp(-2 pi i lane*k2 / n_fft)
+    float* w01;      // [32 * bins_per_lane][2]  piece form of the mel bank (mel_pieces.h)
+    unsigned long long* endmask;  // [32]
+    int* piece0;     // [32]
+    int* pb;         // [n_mels + 2]
+    int n_pieces;
+    int e_bytes;     // per-warp exchange / piece buffer bytes
     // extract launch geometry
     int warps_per_cta;
     int extract_smem_bytes;

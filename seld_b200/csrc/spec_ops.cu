@@ -16,36 +16,37 @@ __host__ __device__ constexpr int sp_align16(int x) { return (x + 15) & ~15; }
 template <int R>
 __global__ void __launch_bounds__(128) complex_spec_kernel(const float* __restrict__ wav, int n_chan, long long n_samples,
                                                            int hop, int t_raw, float scale, const float* __restrict__ window,
-                                                           const float2* __restrict__ twiddle, float2* __restrict__ spec) {
+                                                           const float2* __restrict__ tw_t, float2* __restrict__ spec) {
     using G = Geo<R>;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    float* s_window = reinterpret_cast<float*>(smem);
-    float2* s_twiddle = reinterpret_cast<float2*>(smem + sp_align16(G::N * 4));
-    unsigned char* wp = smem + sp_align16(G::N * 4) + sp_align16(G::N * 8) +
-                        size_t(warp) * (sp_align16(G::E_ELEMS * 8) + sp_align16(G::N * 8));
+    float2* s_tw_t = reinterpret_cast<float2*>(smem);
+    unsigned char* wp = smem + sp_align16(G::N * 8) + size_t(warp) * (sp_align16(G::E_ELEMS * 8) + sp_align16(G::N * 8));
     float2* E = reinterpret_cast<float2*>(wp);
     float2* S = reinterpret_cast<float2*>(wp + sp_align16(G::E_ELEMS * 8));
-    for (int i = threadIdx.x; i < G::N; i += blockDim.x) { s_window[i] = window[i]; s_twiddle[i] = twiddle[i]; }
+    for (int i = threadIdx.x; i < G::N; i += blockDim.x) s_tw_t[i] = tw_t[i];
+    float wreg[R];
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2) wreg[n2] = window[lane + 32 * n2];
     __syncthreads();
-    const Tables tb{s_window, s_twiddle, nullptr, nullptr, nullptr};
+    const Tables tb{nullptr, s_tw_t, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int n_pairs = (n_chan + 1) / 2;
     const long long items = (long long)n_pairs * t_raw;
     ClipSrc src{wav, n_samples, 1, n_samples};
     for (long long it = (long long)blockIdx.x * nwarps + warp; it < items; it += (long long)gridDim.x * nwarps) {
         const int pair = int(it / t_raw), t = int(it % t_raw);
         const int ca = 2 * pair, cb = (2 * pair + 1 < n_chan) ? 2 * pair + 1 : ca;
-        stage1_forward<R>(src, ca, cb, (long long)t * hop - G::N / 2, tb, E, lane);
+        stage1_forward<R, LAYOUT_PLANAR_CL>(src, ca, cb, (long long)t * hop - G::N / 2, wreg, tb, E, lane);
         __syncwarp();
         stage2_forward<R>(E, S, lane);
         __syncwarp();
         float2* oa = spec + ((long long)ca * t_raw + t) * G::F;
         float2* ob = spec + ((long long)cb * t_raw + t) * G::F;
         for (int k = lane; k < G::F; k += 32) {
-            float2 A, B;
-            unpack2(S[k], S[(G::N - k) & (G::N - 1)], A, B);
-            oa[k] = make_float2(A.x * scale, A.y * scale);
-            if (cb != ca) ob[k] = make_float2(B.x * scale, B.y * scale);
+            const float2 z = S[k], zn = S[(G::N - k) & (G::N - 1)];     // Z = FFT(a + i b)
+            const float h = 0.5f * scale;
+            oa[k] = make_float2(h * (z.x + zn.x), h * (z.y - zn.y));
+            if (cb != ca) ob[k] = make_float2(h * (z.y + zn.y), h * (zn.x - z.x));
         }
         __syncwarp();
     }
@@ -111,14 +112,14 @@ static int launch_spec(const seld_plan* plan, const float* wav, int n_chan, long
                        cudaStream_t st) {
     using G = Geo<R>;
     const int warps = (R == 64) ? 2 : 4;
-    const int smem = sp_align16(G::N * 4) + sp_align16(G::N * 8) + warps * (sp_align16(G::E_ELEMS * 8) + sp_align16(G::N * 8));
+    const int smem = sp_align16(G::N * 8) + warps * (sp_align16(G::E_ELEMS * 8) + sp_align16(G::N * 8));
     SELD_CUDA_TRY(cudaFuncSetAttribute(complex_spec_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int t_raw = int(1 + n_samples / plan->hop);
     const long long items = (long long)((n_chan + 1) / 2) * t_raw;
     long long blocks = (items + warps - 1) / warps;
     if (blocks > plan->num_sms * 4) blocks = plan->num_sms * 4;
     complex_spec_kernel<R><<<(int)blocks, warps * 32, smem, st>>>(wav, n_chan, n_samples, plan->hop, t_raw, scale, plan->window,
-                                                                  reinterpret_cast<const float2*>(plan->twiddle),
+                                                                  reinterpret_cast<const float2*>(plan->tw_t),
                                                                   reinterpret_cast<float2*>(spec));
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;

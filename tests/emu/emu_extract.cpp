@@ -8,16 +8,20 @@
 #include <vector>
 
 #include "../../seld_b200/csrc/extract_core.cuh"
+#include "../../seld_b200/csrc/mel_pieces.h"
 
 using namespace seld;
 
-template <int R, int MODE>
-static void run(const float* wav, int layout, int n_clips, long long L, int hop, int n_mels, const Tables& tb,
+template <int R, int MODE, int LAYOUT>
+static void run(const float* wav, int n_clips, long long L, int hop, int n_mels, const Tables& tb,
                 int T_out, float* out, float* clip_max) {
     using G = Geo<R>;
-    const int C = (MODE == MODE_FOA) ? 7 : 10;
+    constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
+    const int layout = LAYOUT;
+    float wreg[32][R];
+    for (int l = 0; l < 32; ++l) for (int n2 = 0; n2 < R; ++n2) wreg[l][n2] = tb.window[l + 32 * n2];
     const int T_raw = 1 + int(L / hop);
-    std::vector<float2> E(G::E_ELEMS), S0(G::N), S1(G::N);
+    std::vector<float2> E(G::E_ELEMS + 4096), S0(G::N), S1(G::N);
     std::vector<float> acc(size_t(n_mels) * C, 0.f);
     for (int clip = 0; clip < n_clips; ++clip) {
         ClipSrc src;
@@ -31,34 +35,44 @@ static void run(const float* wav, int layout, int n_clips, long long L, int hop,
             float* row = (t < T_out) ? out + (size_t(clip) * T_out + t) * n_mels * C : nullptr;
             if (t >= T_raw) { memset(row, 0, sizeof(float) * n_mels * C); continue; }
             const long long start = (long long)t * hop - G::N / 2;
-            for (int l = 0; l < 32; ++l) stage1_forward<R>(src, 0, 1, start, tb, E.data(), l);
+            for (int l = 0; l < 32; ++l) stage1_forward<R, LAYOUT>(src, 0, 1, start, wreg[l], tb, E.data(), l);
             for (int l = 0; l < 32; ++l) stage2_forward<R>(E.data(), S0.data(), l);
-            for (int l = 0; l < 32; ++l) stage1_forward<R>(src, 2, 3, start, tb, E.data(), l);
+            for (int l = 0; l < 32; ++l) stage1_forward<R, LAYOUT>(src, 2, 3, start, wreg[l], tb, E.data(), l);
             for (int l = 0; l < 32; ++l) stage2_forward<R>(E.data(), S1.data(), l);
-            for (int l = 0; l < 32; ++l) bin_phase<R, MODE>(S0.data(), S1.data(), tb, acc.data(), n_mels, C, 1e-8f, l);
+            for (int l = 0; l < 32; ++l) bin_phase<R, MODE>(S0.data(), S1.data(), tb, E.data(), 1e-8f, l);
+            for (int l = 0; l < 32; ++l) cmax = fmaxf(cmax, gather_phase<MODE>(E.data(), tb, acc.data(), n_mels, l));
             if (MODE == MODE_MIC) {
                 for (int l = 0; l < 32; ++l) gcc_stage1<R, 0>(S0.data(), S1.data(), E.data(), l);
-                for (int l = 0; l < 32; ++l) gcc_stage2<R, 0>(E.data(), tb, acc.data(), n_mels, C, l);
+                for (int l = 0; l < 32; ++l) gcc_stage2<R, 0>(E.data(), tb, acc.data(), n_mels, l);
                 for (int l = 0; l < 32; ++l) gcc_stage1<R, 1>(S0.data(), S1.data(), E.data(), l);
-                for (int l = 0; l < 32; ++l) gcc_stage2<R, 1>(E.data(), tb, acc.data(), n_mels, C, l);
+                for (int l = 0; l < 32; ++l) gcc_stage2<R, 1>(E.data(), tb, acc.data(), n_mels, l);
                 for (int l = 0; l < 32; ++l) gcc_stage1<R, 2>(S0.data(), S1.data(), E.data(), l);
-                for (int l = 0; l < 32; ++l) gcc_stage2<R, 2>(E.data(), tb, acc.data(), n_mels, C, l);
+                for (int l = 0; l < 32; ++l) gcc_stage2<R, 2>(E.data(), tb, acc.data(), n_mels, l);
             }
-            for (int l = 0; l < 32; ++l) cmax = fmaxf(cmax, finish_row(acc.data(), n_mels, C, row, l));
+            if (row) for (int l = 0; l < 32; ++l) store_row(acc.data(), n_mels * C, row, l);
         }
         clip_max[clip] = cmax;
     }
 }
 
 extern "C" int emu_extract(const float* wav, int layout, int n_clips, long long L, int n_fft, int hop, int n_mels,
-                           int mode, const float* window, const float* twiddle, const int* seg, const float* w0,
-                           const float* w1, int T_out, float* out, float* clip_max) {
-    Tables tb{window, reinterpret_cast<const float2*>(twiddle), seg, w0, w1};
-#define GO(RR)                                                                                             \
-    if (n_fft == 32 * RR) {                                                                                \
-        if (mode == MODE_FOA) run<RR, MODE_FOA>(wav, layout, n_clips, L, hop, n_mels, tb, T_out, out, clip_max); \
-        else run<RR, MODE_MIC>(wav, layout, n_clips, L, hop, n_mels, tb, T_out, out, clip_max);            \
-        return 0;                                                                                          \
+                           int mode, const float* window, const float* twiddle, const float* mel_fb, int T_out,
+                           float* out, float* clip_max) {
+    // lane-contiguous twiddle table tw_t[k2*32 + lane] = W^(lane*k2), as seld_plan_create builds it
+    const float2* lin = reinterpret_cast<const float2*>(twiddle);
+    std::vector<float2> tw_t(n_fft);
+    for (int k2 = 0; k2 < n_fft / 32; ++k2)
+        for (int l = 0; l < 32; ++l) tw_t[k2 * 32 + l] = lin[(l * k2) % n_fft];
+    MelPieces mp;
+    if (!build_mel_pieces(mel_fb, n_fft / 2 + 1, n_mels, mp).empty()) return -2;
+    Tables tb{window, tw_t.data(), lin, reinterpret_cast<const float2*>(mp.w01.data()), mp.endmask.data(), mp.piece0.data(),
+              mp.pb.data()};
+#define GO3(RR, MM, LL) run<RR, MM, LL>(wav, n_clips, L, hop, n_mels, tb, T_out, out, clip_max)
+#define GO(RR)                                                                   \
+    if (n_fft == 32 * RR) {                                                      \
+        if (mode == MODE_FOA) { if (layout == 0) GO3(RR, MODE_FOA, 0); else GO3(RR, MODE_FOA, 1); } \
+        else { if (layout == 0) GO3(RR, MODE_MIC, 0); else GO3(RR, MODE_MIC, 1); } \
+        return 0;                                                                \
     }
     GO(8) GO(16) GO(32) GO(64)
     return -1;
