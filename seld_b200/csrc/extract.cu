@@ -217,7 +217,7 @@ static int launch_extract(const seld_plan* plan, const ExtractArgs& a, cudaStrea
 template <int R, int MODE>
 static void plan_geometry_mode(seld_plan* plan) {
     using G = Geo<R>;
-    const int pstride = (MODE == MODE_FOA) ? 64 : 32;
+    const int pstride = PieceGeo<MODE>::PSTRIDE * 8;
     int e_bytes = align16(G::E_ELEMS * 8);
     if (plan->n_pieces * pstride > e_bytes) e_bytes = align16(plan->n_pieces * pstride);
     plan->e_bytes = e_bytes;

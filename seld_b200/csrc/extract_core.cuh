@@ -245,28 +245,70 @@ SELD_HD float2 unit_phasor(float2 a) {   // a / |a|, (0,0) for a == 0; scaled so
     return make_float2(x * r, y * r);
 }
 
-SELD_HD float fast_rsqrt(float s) {
-#if defined(__CUDA_ARCH__)
-    return rsqrtf(s);
-#else
-    return 1.0f / sqrtf(s);
-#endif
-}
-
 // ---------------------------------------------------------------- bin phase
 // NV = 7 (FOA: 4 powers + 3 normalised intensity components) or 4 (MIC: powers; unit phasors are
 // written back in place of the packed spectra for the GCC phase).  With Z = FFT(a + i b):
 // 2 A[k] = Z[k] + conj(Z[N-k]), 2 B[k] = -i (Z[k] - conj(Z[N-k])); the factor 2 is carried: powers come out
 // 4x (the mel weights are pre-scaled by the exact constant 1/4) and the intensity vector, scale-free apart from
-// eps, is produced 4x as well.  Each lane walks its BPT contiguous bins in straight-line code, accumulating
-// (into filter seg, into filter seg+1) as one packed FFMA2 per channel, and stores the pair sums at the end of every
-// piece: P[piece][c] = (sum w0 val_c, sum w1 val_c).  No atomics, fixed order => bit-reproducible.
+// eps, is produced 4x as well.  Each lane walks its BPT contiguous bins in straight-line, branch-free code,
+// accumulating (into filter seg, into filter seg+1) as one packed FFMA2 per channel; at the end of every piece the
+// pair sums are stored (predicated) as one record P[piece][c] = (sum w0 val_c, sum w1 val_c) and the accumulators
+// are cleared.  Records are PSTRIDE = 7 | 5 float2 apart: 14 | 10 words, so 16 neighbouring pieces hit 16 different
+// bank pairs.  No atomics, fixed order => bit-reproducible.
+template <int MODE>
+struct PieceGeo {
+    static constexpr int NV = (MODE == MODE_FOA) ? 7 : 4;
+    static constexpr int PSTRIDE = (MODE == MODE_FOA) ? 7 : 5;      // float2 per piece record
+};
+
+SELD_HD float rsqrt_ftz(float s) {      // one MUFU.RSQ; subnormal inputs flush to 0 -> +inf (callers clamp)
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    return r;
+#else
+    return (s < 1.17549435e-38f) ? INFINITY : 1.0f / sqrtf(s);
+#endif
+}
+
+// if (flag) { rec[c] = acc[c] for c < NV; acc[c] = 0; }   -- predicated, no branch
+template <int NV>
+SELD_HD void piece_flush(float2* acc, float2* rec, unsigned flag) {
+#if defined(__CUDA_ARCH__)
+    const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(rec));
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(acc);
+    if constexpr (NV == 7) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %7, 0;\n\t"
+            "@p st.shared.b64 [%8], %0;\n\t@p st.shared.b64 [%8+8], %1;\n\t@p st.shared.b64 [%8+16], %2;\n\t"
+            "@p st.shared.b64 [%8+24], %3;\n\t@p st.shared.b64 [%8+32], %4;\n\t@p st.shared.b64 [%8+40], %5;\n\t"
+            "@p st.shared.b64 [%8+48], %6;\n\t"
+            "@p mov.b64 %0, 0;\n\t@p mov.b64 %1, 0;\n\t@p mov.b64 %2, 0;\n\t@p mov.b64 %3, 0;\n\t"
+            "@p mov.b64 %4, 0;\n\t@p mov.b64 %5, 0;\n\t@p mov.b64 %6, 0;\n\t}"
+            : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3]), "+l"(a[4]), "+l"(a[5]), "+l"(a[6])
+            : "r"(flag), "r"(addr));
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
+            "@p st.shared.b64 [%5], %0;\n\t@p st.shared.b64 [%5+8], %1;\n\t@p st.shared.b64 [%5+16], %2;\n\t"
+            "@p st.shared.b64 [%5+24], %3;\n\t"
+            "@p mov.b64 %0, 0;\n\t@p mov.b64 %1, 0;\n\t@p mov.b64 %2, 0;\n\t@p mov.b64 %3, 0;\n\t}"
+            : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3])
+            : "r"(flag), "r"(addr));
+    }
+#else
+    if (flag) {
+        for (int c = 0; c < NV; ++c) { rec[c] = acc[c]; acc[c] = make_float2(0.f, 0.f); }
+    }
+#endif
+}
+
 template <int R, int MODE>
 SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, float eps, int lane) {
     using G = Geo<R>;
     constexpr int N = G::N;
-    constexpr int NV = (MODE == MODE_FOA) ? 7 : 4;
-    constexpr int PSTRIDE = (MODE == MODE_FOA) ? 8 : 4;         // float2 per piece record (64 B / 32 B)
+    constexpr int NV = PieceGeo<MODE>::NV;
+    constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
     const int kbeg = lane * G::BPT;
     const unsigned long long endmask = tb.endmask[lane];
     int piece = tb.piece0[lane];
@@ -277,29 +319,30 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
 
 #pragma unroll
     for (int i = 0; i < G::BPT; ++i) {
-        const int k = kbeg + i;
-        if (k < G::F) {
-            const int kn = (N - k) & (N - 1);
-            const float2 z0 = S0[k], z0n = S0[kn], z1 = S1[k], z1n = S1[kn];
-            float2 ch[4];                                  // twice the channel spectra
-            ch[0] = make_float2(z0.x + z0n.x, z0.y - z0n.y);
-            ch[1] = make_float2(z0.y + z0n.y, z0n.x - z0.x);
-            ch[2] = make_float2(z1.x + z1n.x, z1.y - z1n.y);
-            ch[3] = make_float2(z1.y + z1n.y, z1n.x - z1.x);
-            float val[NV];
+        const bool valid = kbeg + i < G::F;
+        const int k = valid ? kbeg + i : G::F - 1;       // bins past F-1 carry zero weights: recompute the last bin
+        const int kn = (N - k) & (N - 1);
+        const float2 z0 = S0[k], z0n = S0[kn], z1 = S1[k], z1n = S1[kn];
+        float2 ch[4];                                  // twice the channel spectra
+        ch[0] = make_float2(z0.x + z0n.x, z0.y - z0n.y);
+        ch[1] = make_float2(z0.y + z0n.y, z0n.x - z0.x);
+        ch[2] = make_float2(z1.x + z1n.x, z1.y - z1n.y);
+        ch[3] = make_float2(z1.y + z1n.y, z1n.x - z1.x);
+        float val[NV];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) val[c] = fmaf(ch[c].x, ch[c].x, ch[c].y * ch[c].y);     // 4 |X_c|^2
-            if constexpr (MODE == MODE_FOA) {
-                // W = ch0, Y = ch1, Z = ch2, X = ch3; I = Re(conj(W) * {X, Y, Z})  (here 4 I)
-                const float ix = fmaf(ch[0].x, ch[3].x, ch[0].y * ch[3].y);
-                const float iy = fmaf(ch[0].x, ch[1].x, ch[0].y * ch[1].y);
-                const float iz = fmaf(ch[0].x, ch[2].x, ch[0].y * ch[2].y);
-                // 4 / max(|4 I|, 4 eps) = min(4 rsqrt(|4 I|^2), 1/eps); rsqrt(0) = inf -> 1/eps, as maximum(norm, eps)
-                const float inv4 = fminf(4.0f * fast_rsqrt(fmaf(ix, ix, fmaf(iy, iy, iz * iz))), inv_eps);
-                val[4] = ix * inv4;
-                val[5] = iy * inv4;
-                val[6] = iz * inv4;
-            } else {
+        for (int c = 0; c < 4; ++c) val[c] = fmaf(ch[c].x, ch[c].x, ch[c].y * ch[c].y);     // 4 |X_c|^2
+        if constexpr (MODE == MODE_FOA) {
+            // W = ch0, Y = ch1, Z = ch2, X = ch3; I = Re(conj(W) * {X, Y, Z})  (here 4 I)
+            const float ix = fmaf(ch[0].x, ch[3].x, ch[0].y * ch[3].y);
+            const float iy = fmaf(ch[0].x, ch[1].x, ch[0].y * ch[1].y);
+            const float iz = fmaf(ch[0].x, ch[2].x, ch[0].y * ch[2].y);
+            // 4 / max(|4 I|, 4 eps) = min(4 rsqrt(|4 I|^2), 1/eps); rsqrt(0) = inf -> 1/eps, as maximum(norm, eps)
+            const float inv4 = fminf(4.0f * rsqrt_ftz(fmaf(ix, ix, fmaf(iy, iy, iz * iz))), inv_eps);
+            val[4] = ix * inv4;
+            val[5] = iy * inv4;
+            val[6] = iz * inv4;
+        } else {
+            if (valid) {
                 const float2 u0 = unit_phasor(ch[0]), u1 = unit_phasor(ch[1]);
                 const float2 u2 = unit_phasor(ch[2]), u3 = unit_phasor(ch[3]);
                 if (k == 0 || k == N / 2) {          // real bins: both channels of a pair share one slot
@@ -310,25 +353,13 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
                     S1[k] = u2; S1[kn] = u3;
                 }
             }
-            const float2 w = tb.w01[k];
-#pragma unroll
-            for (int c = 0; c < NV; ++c) acc2[c] = pfma(make_float2(val[c], val[c]), w, acc2[c]);
         }
-        if ((endmask >> i) & 1ull) {
-            float4* dst = reinterpret_cast<float4*>(P + piece * PSTRIDE);
+        const float2 w = tb.w01[kbeg + i];
 #pragma unroll
-            for (int c = 0; c + 1 < NV; c += 2) {
-                float4 q; q.x = acc2[c].x; q.y = acc2[c].y; q.z = acc2[c + 1].x; q.w = acc2[c + 1].y;
-                dst[c / 2] = q;
-            }
-            if constexpr (NV & 1) {
-                float4 q; q.x = acc2[NV - 1].x; q.y = acc2[NV - 1].y; q.z = 0.f; q.w = 0.f;
-                dst[NV / 2] = q;
-            }
-            ++piece;
-#pragma unroll
-            for (int c = 0; c < NV; ++c) acc2[c] = make_float2(0.f, 0.f);
-        }
+        for (int c = 0; c < NV; ++c) acc2[c] = pfma(make_float2(val[c], val[c]), w, acc2[c]);
+        const unsigned flag = static_cast<unsigned>(endmask >> i) & 1u;
+        piece_flush<NV>(acc2, P + piece * PSTRIDE, flag);
+        piece += int(flag);
     }
 }
 
@@ -345,19 +376,21 @@ SELD_HD float fast_db(float x) {            // 10 log10(x), x > 0
 // order.  Log-mel channels get 10 log10(max(., 1e-10)) here; returns the lane's maximum dB.
 template <int MODE>
 SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_mels, int lane) {
-    constexpr int NV = (MODE == MODE_FOA) ? 7 : 4;
+    constexpr int NV = PieceGeo<MODE>::NV;
+    constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
-    constexpr int PSTRIDE = (MODE == MODE_FOA) ? 8 : 4;
     float mx = -INFINITY;
     for (int m = lane; m < n_mels; m += 32) {
         const int p0 = tb.pb[m], p1 = tb.pb[m + 1], p2 = tb.pb[m + 2];
         float sum[NV];
 #pragma unroll
         for (int c = 0; c < NV; ++c) sum[c] = 0.f;
+#pragma unroll 1
         for (int p = p0; p < p1; ++p) {                // falling slopes of the segment below
 #pragma unroll
             for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].y;
         }
+#pragma unroll 1
         for (int p = p1; p < p2; ++p) {                // rising slopes of this filter's own segment
 #pragma unroll
             for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].x;
@@ -479,7 +512,13 @@ SELD_HD void gcc_stage2(const float2* E, const Tables& tb, float* acc, int n_mel
 // ---------------------------------------------------------------- finish one frame row
 // Coalesced copy of the staged row acc[m * C + c] to global memory.
 SELD_HD void store_row(const float* acc, int row_elems, float* out_row, int lane) {
-    for (int e = lane; e < row_elems; e += 32) out_row[e] = acc[e];
+    if ((row_elems & 3) == 0 && (reinterpret_cast<uintptr_t>(out_row) & 15) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(acc);
+        float4* d4 = reinterpret_cast<float4*>(out_row);
+        for (int e = lane; e < row_elems / 4; e += 32) d4[e] = s4[e];
+    } else {
+        for (int e = lane; e < row_elems; e += 32) out_row[e] = acc[e];
+    }
 }
 
 }  // namespace seld
