@@ -18,7 +18,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -43,45 +42,57 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle-reason samples during the timed region, read through NVML in a background thread
+    (the fields of the B200_PROFILING.md recipe).  NVML is used instead of a looping `nvidia-smi` process because
+    the latter's driver queries measurably stall kernel launches (sporadic 2-10x slow steps in per-launch timings)."""
+    REASONS = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.05):
+        self.index, self.period, self.samples, self.err = index, period_s, [], None
+        self._stop = threading.Event()
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
-                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(visible.split(',')[self.index]) if visible and visible.replace(',', '').isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as exc:           # noqa: BLE001
+            self.err = str(exc)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:          # noqa: BLE001  older binding name
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, reasons))
+            except Exception as exc:       # noqa: BLE001
+                self.err = str(exc)
+                return
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.thread is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [f'nvml unavailable: {self.err}']}
+        self._stop.set()
         self.thread.join(timeout=2)
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx = float(r[2])
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        busy = sorted(sm)[len(sm) // 2:] if sm else []     # the upper half = samples taken under load
-        return {'sm_mhz': statistics.median(busy) if busy else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+        sm = sorted(m for m, _ in self.samples)
+        mask = 0
+        for _, r in self.samples:
+            mask |= r
+        reasons = sorted(k for k, bit in self.REASONS.items() if mask & bit)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': self.max_mhz, 'reasons': reasons,
+                'samples': len(sm), 'how': 'NVML, 50 ms period, during the timed region'}
 
 
 def cpu_port_sample(mode, n_clips, threads=None):
@@ -143,7 +154,7 @@ def workload_config(args, clips):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mode', default='foa', choices=['foa', 'mic'])

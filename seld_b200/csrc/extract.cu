@@ -43,6 +43,7 @@ struct ExtractArgs {
     const int* pb;
     int hop, n_mels;
     int e_bytes;              // per-warp exchange / piece buffer size
+    int gather_unrolled;      // every mel segment has <= 3 pieces and n_mels <= 64: gather_pairs
     int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
     long long n_super;        // super-chunks of warps_per_cta * kFramesPerWarp frames
 };
@@ -55,7 +56,7 @@ __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 template <int R, int MODE>
 __host__ __device__ constexpr int table_bytes(int n_mels) {
     using G = Geo<R>;
-    return align16(G::N * 8) + align16(32 * G::BPT * 8) + align16(32 * 8) + align16(32 * 4) + align16((n_mels + 2) * 4) +
+    return align16(G::N * 8) + align16(32 * G::BPT * 8) + align16(32 * 8) + align16(32 * 4) + align16((n_mels + 2) * 4) + 64 +
            (MODE == MODE_MIC ? align16(G::N * 8) : 0);
 }
 template <int R, int MODE>
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     unsigned long long* s_endmask = reinterpret_cast<unsigned long long*>(p);  p += align16(32 * 8);
     int* s_piece0 = reinterpret_cast<int*>(p);  p += align16(32 * 4);
     int* s_pb = reinterpret_cast<int*>(p);  p += align16((a.n_mels + 2) * 4);
+    float2* s_zero = reinterpret_cast<float2*>(p);  p += 64;
     float2* s_tw_lin = nullptr;
     if constexpr (MODE == MODE_MIC) { s_tw_lin = reinterpret_cast<float2*>(p);  p += align16(G::N * 8); }
     for (int i = threadIdx.x; i < G::N; i += blockDim.x) {
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     for (int i = threadIdx.x; i < 32 * G::BPT; i += blockDim.x) s_w01[i] = a.w01[i];
     for (int i = threadIdx.x; i < a.n_mels + 2; i += blockDim.x) s_pb[i] = a.pb[i];
     if (threadIdx.x < 32) { s_endmask[threadIdx.x] = a.endmask[threadIdx.x]; s_piece0[threadIdx.x] = a.piece0[threadIdx.x]; }
+    if (threadIdx.x < 8) s_zero[threadIdx.x] = make_float2(0.f, 0.f);
     // ---- per-warp regions
     const int wbytes = warp_bytes<R, MODE>(a.n_mels, a.e_bytes);
     unsigned char* wp = p + size_t(warp) * wbytes;
@@ -109,74 +112,131 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     for (int n2 = 0; n2 < R; ++n2) wreg[n2] = a.window[lane + 32 * n2];
     __syncthreads();
 
-    const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_piece0, s_pb};
+    const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_piece0, s_pb, s_zero};
     const long long total_frames = (long long)a.n_clips * a.frames_per_clip;
 
     float run_max = -INFINITY;
     int run_clip = -1;
 
-    for (long long sc = blockIdx.x; sc < a.n_super; sc += gridDim.x) {
-        const long long g0 = (sc * nwarps + warp) * kFramesPerWarp;
-        for (int i = 0; i < kFramesPerWarp; ++i) {
-            const long long g = g0 + i;
-            if (g >= total_frames) break;
-            const int clip = int(g / a.frames_per_clip);
-            const int j = int(g - (long long)clip * a.frames_per_clip);
-            int t;
-            if constexpr (EDGE) t = (j < a.t_lo) ? j : a.t_hi + (j - a.t_lo);
-            else t = a.t_lo + j;
-            float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
-            if constexpr (EDGE) {
+    // everything after the two packed FFTs of a frame: mel pieces, gather, (GCC), row store, running clip maximum
+    auto finish_frame = [&](int clip, float* row) {
+        bin_phase<R, MODE>(S0, S1, tb, E, 1e-8f, lane);
+        __syncwarp();
+        float mx = a.gather_unrolled ? gather_pairs<MODE>(E, tb, acc, a.n_mels, lane)
+                                     : gather_phase<MODE, 0>(E, tb, acc, a.n_mels, lane);
+        __syncwarp();
+        if constexpr (MODE == MODE_MIC) {
+            gcc_stage1<R, 0>(S0, S1, E, lane);
+            __syncwarp();
+            gcc_stage2<R, 0>(E, tb, acc, a.n_mels, lane);
+            __syncwarp();
+            gcc_stage1<R, 1>(S0, S1, E, lane);
+            __syncwarp();
+            gcc_stage2<R, 1>(E, tb, acc, a.n_mels, lane);
+            __syncwarp();
+            gcc_stage1<R, 2>(S0, S1, E, lane);
+            __syncwarp();
+            gcc_stage2<R, 2>(E, tb, acc, a.n_mels, lane);
+            __syncwarp();
+        }
+        if (row != nullptr) store_row(acc, row_elems, row, lane);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (clip != run_clip) {
+            if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], float_to_key(run_max));
+            run_clip = clip;
+            run_max = -INFINITY;
+        }
+        run_max = fmaxf(run_max, mx);
+        __syncwarp();
+    };
+
+    if constexpr (EDGE) {
+        for (long long sc = blockIdx.x; sc < a.n_super; sc += gridDim.x) {
+            const long long g0 = (sc * nwarps + warp) * kFramesPerWarp;
+            for (int i = 0; i < kFramesPerWarp; ++i) {
+                const long long g = g0 + i;
+                if (g >= total_frames) break;
+                const int clip = int(g / a.frames_per_clip);
+                const int j = int(g - (long long)clip * a.frames_per_clip);
+                const int t = (j < a.t_lo) ? j : a.t_hi + (j - a.t_lo);
+                float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
                 if (t >= a.t_raw) {                   // zero padding rows (reference :142-145)
                     for (int e = lane; e < row_elems; e += 32) row[e] = 0.f;
                     continue;
                 }
+                ClipSrc src;
+                src.base = a.wav + (long long)clip * 4 * a.n_samples;
+                src.n_samples = a.n_samples;
+                if (a.layout == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
+                else { src.chan_stride = 1; src.samp_stride = 4; }
+                const long long start = (long long)t * a.hop - G::N / 2;
+#pragma unroll 1
+                for (int pr = 0; pr < 2; ++pr) {
+                    float2 v[R];
+                    stage1_load_reflect<R>(src, 2 * pr, 2 * pr + 1, start, wreg, v, lane);
+                    stage1_fft_store<R>(v, tb, E, lane);
+                    __syncwarp();
+                    stage2_forward<R>(E, pr ? S1 : S0, lane);
+                    __syncwarp();
+                }
+                finish_frame(clip, row);
             }
-            if (clip != run_clip) {
-                if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], float_to_key(run_max));
-                run_clip = clip;
-                run_max = -INFINITY;
-            }
-            ClipSrc src;
+        }
+    } else {
+        // Interior frames, software-pipelined over half-frames (one channel pair each): the raw samples of the NEXT
+        // half-frame are requested before the current one's FFT starts, so HBM/L2 latency hides behind the arithmetic.
+        long long sc = blockIdx.x;
+        int fi = 0;
+        auto frame_index = [&](long long s, int i) -> long long {       // -1 past the end
+            if (s >= a.n_super) return -1;
+            const long long g = (s * nwarps + warp) * kFramesPerWarp + i;
+            return g < total_frames ? g : -1;
+        };
+        auto source_of = [&](long long g, ClipSrc& src, long long& start, int& clip, int& t) {
+            clip = int(g / a.frames_per_clip);
+            t = a.t_lo + int(g - (long long)clip * a.frames_per_clip);
             src.base = a.wav + (long long)clip * 4 * a.n_samples;
             src.n_samples = a.n_samples;
-            if ((EDGE ? a.layout : LAYOUT) == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
+            if constexpr (LAYOUT == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
             else { src.chan_stride = 1; src.samp_stride = 4; }
-            const long long start = (long long)t * a.hop - G::N / 2;
-
+            start = (long long)t * a.hop - G::N / 2;
+        };
+        long long g = frame_index(sc, fi);
+        float2 raw[R];
+        ClipSrc src;
+        long long start = 0;
+        int clip = 0, t = 0;
+        if (g >= 0) {
+            source_of(g, src, start, clip, t);
+            stage1_load_raw<R, LAYOUT>(src, 0, 1, start, raw, lane);
+        }
+        int pr = 0;
 #pragma unroll 1
-            for (int pr = 0; pr < 2; ++pr) {          // channel pairs (0,1) and (2,3); not unrolled: code size
-                float2 v[R];
-                if constexpr (EDGE) stage1_load_reflect<R>(src, 2 * pr, 2 * pr + 1, start, wreg, v, lane);
-                else stage1_load_interior<R, LAYOUT>(src, 2 * pr, 2 * pr + 1, start, wreg, v, lane);
-                stage1_fft_store<R>(v, tb, E, lane);
-                __syncwarp();
-                stage2_forward<R>(E, pr ? S1 : S0, lane);
-                __syncwarp();
+        while (g >= 0) {
+            float2 v[R];
+            apply_window<R>(raw, wreg, v);
+            // request the next half-frame
+            long long g_next = g;
+            if (pr == 0) {
+                stage1_load_raw<R, LAYOUT>(src, 2, 3, start, raw, lane);
+            } else {
+                if (++fi == kFramesPerWarp) { fi = 0; sc += gridDim.x; }
+                g_next = frame_index(sc, fi);
             }
-            bin_phase<R, MODE>(S0, S1, tb, E, 1e-8f, lane);
-            __syncwarp();
-            float mx = gather_phase<MODE>(E, tb, acc, a.n_mels, lane);
-            __syncwarp();
-            if constexpr (MODE == MODE_MIC) {
-                gcc_stage1<R, 0>(S0, S1, E, lane);
-                __syncwarp();
-                gcc_stage2<R, 0>(E, tb, acc, a.n_mels, lane);
-                __syncwarp();
-                gcc_stage1<R, 1>(S0, S1, E, lane);
-                __syncwarp();
-                gcc_stage2<R, 1>(E, tb, acc, a.n_mels, lane);
-                __syncwarp();
-                gcc_stage1<R, 2>(S0, S1, E, lane);
-                __syncwarp();
-                gcc_stage2<R, 2>(E, tb, acc, a.n_mels, lane);
-                __syncwarp();
+            const int clip_now = clip;
+            float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
+            if (pr == 1 && g_next >= 0) {
+                source_of(g_next, src, start, clip, t);
+                stage1_load_raw<R, LAYOUT>(src, 0, 1, start, raw, lane);
             }
-            if (row != nullptr) store_row(acc, row_elems, row, lane);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            run_max = fmaxf(run_max, mx);
+            stage1_fft_store<R>(v, tb, E, lane);
             __syncwarp();
+            stage2_forward<R>(E, pr ? S1 : S0, lane);
+            __syncwarp();
+            if (pr == 1) finish_frame(clip_now, row);
+            g = g_next;
+            pr ^= 1;
         }
     }
     if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], float_to_key(run_max));
@@ -308,6 +368,7 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
         return SELD_EUNSUPPORTED;
     }
     plan->n_pieces = mp.n_pieces;
+    plan->max_pieces_per_seg = mp.max_pieces_per_seg;
     std::vector<float> tw(2 * (size_t)n_fft);
     for (int j = 0; j < n_fft; ++j) {
         const double ang = -2.0 * 3.14159265358979323846264338327950288 * double(j) / double(n_fft);
@@ -403,6 +464,7 @@ int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips
     a.piece0 = plan->piece0;
     a.pb = plan->pb;
     a.e_bytes = plan->e_bytes;
+    a.gather_unrolled = plan->max_pieces_per_seg <= 3 && plan->n_mels <= 64;
     // frames [t_lo, t_hi) need no reflection: t*hop - n_fft/2 >= 0 and t*hop + n_fft/2 <= n_samples
     {
         const long long half = plan->n_fft / 2;

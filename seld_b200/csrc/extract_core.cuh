@@ -40,6 +40,7 @@ struct Tables {             // CTA-shared constant tables (shared memory on the 
     const unsigned long long* endmask;  // [32] bit i set: bin l*BPT + i is the last bin of a piece
     const int* piece0;          // [32]     index of lane l's first piece
     const int* pb;              // [n_mels + 2] pieces with seg == m are [pb[m+1], pb[m+2])
+    const float2* zero_rec;     // [8] zeros: a piece record that contributes nothing
 };
 
 struct ClipSrc {            // one clip's samples: channel c, sample i -> base[c * chan_stride + i * samp_stride]
@@ -149,21 +150,31 @@ SELD_HD void pfft_dif(float2* v) {
 // Interior frames (whole frame inside the clip, no reflection): one 64-bit load per tap when the two channels
 // of the pair are adjacent in memory (interleaved layout, ch_b == ch_a + 1, ch_a even), else two 32-bit loads.
 template <int R, int LAYOUT>
-SELD_HD void stage1_load_interior(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, const float* wreg,
-                                  float2* v, int lane) {
+SELD_HD void stage1_load_raw(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, float2* raw, int lane) {
     if constexpr (LAYOUT == LAYOUT_INTERLEAVED_LC) {
         const float2* p = reinterpret_cast<const float2*>(src.base + (frame_start + lane) * 4 + ch_a);
 #pragma unroll
-        for (int n2 = 0; n2 < R; ++n2) {
-            const float2 s = p[64 * n2];
-            v[n2] = make_float2(wreg[n2] * s.x, wreg[n2] * s.y);
-        }
+        for (int n2 = 0; n2 < R; ++n2) raw[n2] = p[64 * n2];
     } else {
         const float* pa = src.base + ch_a * src.chan_stride + frame_start + lane;       // planar: samp_stride == 1
         const float* pb = src.base + ch_b * src.chan_stride + frame_start + lane;
 #pragma unroll
-        for (int n2 = 0; n2 < R; ++n2) v[n2] = make_float2(wreg[n2] * pa[32 * n2], wreg[n2] * pb[32 * n2]);
+        for (int n2 = 0; n2 < R; ++n2) raw[n2] = make_float2(pa[32 * n2], pb[32 * n2]);
     }
+}
+
+template <int R>
+SELD_HD void apply_window(const float2* raw, const float* wreg, float2* v) {
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2) v[n2] = pmul(raw[n2], make_float2(wreg[n2], wreg[n2]));
+}
+
+template <int R, int LAYOUT>
+SELD_HD void stage1_load_interior(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, const float* wreg,
+                                  float2* v, int lane) {
+    float2 raw[R];
+    stage1_load_raw<R, LAYOUT>(src, ch_a, ch_b, frame_start, raw, lane);
+    apply_window<R>(raw, wreg, v);
 }
 
 // Edge frames: reflect without edge repeat (torch.stft center=True, pad_mode='reflect').
@@ -271,31 +282,29 @@ SELD_HD float rsqrt_ftz(float s) {      // one MUFU.RSQ; subnormal inputs flush 
 #endif
 }
 
-// if (flag) { rec[c] = acc[c] for c < NV; acc[c] = 0; }   -- predicated, no branch
+// if (flag) rec[c] = acc[c] for c < NV (predicated stores, no branch); then acc[c] *= (flag ? 0 : 1)
 template <int NV>
 SELD_HD void piece_flush(float2* acc, float2* rec, unsigned flag) {
 #if defined(__CUDA_ARCH__)
     const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(rec));
-    unsigned long long* a = reinterpret_cast<unsigned long long*>(acc);
+    const unsigned long long* a = reinterpret_cast<const unsigned long long*>(acc);
     if constexpr (NV == 7) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %7, 0;\n\t"
             "@p st.shared.b64 [%8], %0;\n\t@p st.shared.b64 [%8+8], %1;\n\t@p st.shared.b64 [%8+16], %2;\n\t"
             "@p st.shared.b64 [%8+24], %3;\n\t@p st.shared.b64 [%8+32], %4;\n\t@p st.shared.b64 [%8+40], %5;\n\t"
-            "@p st.shared.b64 [%8+48], %6;\n\t"
-            "@p mov.b64 %0, 0;\n\t@p mov.b64 %1, 0;\n\t@p mov.b64 %2, 0;\n\t@p mov.b64 %3, 0;\n\t"
-            "@p mov.b64 %4, 0;\n\t@p mov.b64 %5, 0;\n\t@p mov.b64 %6, 0;\n\t}"
-            : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3]), "+l"(a[4]), "+l"(a[5]), "+l"(a[6])
-            : "r"(flag), "r"(addr));
+            "@p st.shared.b64 [%8+48], %6;\n\t}"
+            :: "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "r"(flag), "r"(addr));
     } else {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
             "@p st.shared.b64 [%5], %0;\n\t@p st.shared.b64 [%5+8], %1;\n\t@p st.shared.b64 [%5+16], %2;\n\t"
-            "@p st.shared.b64 [%5+24], %3;\n\t"
-            "@p mov.b64 %0, 0;\n\t@p mov.b64 %1, 0;\n\t@p mov.b64 %2, 0;\n\t@p mov.b64 %3, 0;\n\t}"
-            : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3])
-            : "r"(flag), "r"(addr));
+            "@p st.shared.b64 [%5+24], %3;\n\t}"
+            :: "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "r"(flag), "r"(addr));
     }
+    const float keep = __uint_as_float((flag ^ 1u) * 0x3f800000u);      // 1.0f or 0.0f
+#pragma unroll
+    for (int c = 0; c < NV; ++c) acc[c] = pmul(acc[c], make_float2(keep, keep));
 #else
     if (flag) {
         for (int c = 0; c < NV; ++c) { rec[c] = acc[c]; acc[c] = make_float2(0.f, 0.f); }
@@ -374,7 +383,7 @@ SELD_HD float fast_db(float x) {            // 10 log10(x), x > 0
 // ---------------------------------------------------------------- gather: pieces -> mel rows
 // Lane l owns filters m = l, l + 32, ...: mel[m][c] = sum_{pieces of seg m} P.x + sum_{pieces of seg m-1} P.y, in piece
 // order.  Log-mel channels get 10 log10(max(., 1e-10)) here; returns the lane's maximum dB.
-template <int MODE>
+template <int MODE, int MAXP>
 SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_mels, int lane) {
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
@@ -385,15 +394,33 @@ SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_
         float sum[NV];
 #pragma unroll
         for (int c = 0; c < NV; ++c) sum[c] = 0.f;
-#pragma unroll 1
-        for (int p = p0; p < p1; ++p) {                // falling slopes of the segment below
+        if constexpr (MAXP > 0) {
+            // at most MAXP pieces per segment (checked when the plan is built): straight-line, independent loads
 #pragma unroll
-            for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].y;
-        }
-#pragma unroll 1
-        for (int p = p1; p < p2; ++p) {                // rising slopes of this filter's own segment
+            for (int j = 0; j < MAXP; ++j) {
+                const bool on = p0 + j < p1;
+                const int p = on ? p0 + j : p0;
 #pragma unroll
-            for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].x;
+                for (int c = 0; c < NV; ++c) { const float t = P[p * PSTRIDE + c].y; sum[c] += on ? t : 0.f; }
+            }
+#pragma unroll
+            for (int j = 0; j < MAXP; ++j) {
+                const bool on = p1 + j < p2;
+                const int p = on ? p1 + j : p1;
+#pragma unroll
+                for (int c = 0; c < NV; ++c) { const float t = P[p * PSTRIDE + c].x; sum[c] += on ? t : 0.f; }
+            }
+        } else {
+#pragma unroll 1
+            for (int p = p0; p < p1; ++p) {                // falling slopes of the segment below
+#pragma unroll
+                for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].y;
+            }
+#pragma unroll 1
+            for (int p = p1; p < p2; ++p) {                // rising slopes of this filter's own segment
+#pragma unroll
+                for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].x;
+            }
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -406,6 +433,74 @@ SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_
     }
     return mx;
 }
+
+// Fast gather for n_mels <= 64 and <= 3 pieces per segment: lane l totals the pieces of segments 2l and 2l+1 with
+// packed adds (missing pieces read an all-zero record), so mel[2l+1] = A[2l+1].x + A[2l].y stays inside the lane and
+// mel[2l] = A[2l].x + A[2l-1].y needs one shuffle from lane l-1 per channel.
+template <int MODE>
+SELD_HD float gather_pairs(const float2* P, const Tables& tb, float* acc, int n_mels, int lane
+#if !defined(__CUDA_ARCH__)
+                           , float2* xchg      // host emulation of the shuffle: [32][NV] (A[2l+1].y of every lane)
+#endif
+) {
+    constexpr int NV = PieceGeo<MODE>::NV;
+    constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
+    constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
+    float2 A[2][NV];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int s = 2 * lane + h;
+        const int ps = (s < n_mels) ? tb.pb[s + 1] : 0, pe = (s < n_mels) ? tb.pb[s + 2] : 0;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) A[h][c] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float2* rec = (ps + j < pe) ? P + (ps + j) * PSTRIDE : tb.zero_rec;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) A[h][c] = padd(A[h][c], rec[c]);
+        }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+#if defined(__CUDA_ARCH__)
+        float below = __shfl_up_sync(0xffffffffu, A[1][c].y, 1);
+#else
+        float below = (lane > 0) ? xchg[(lane - 1) * NV + c].y : 0.f;
+#endif
+        if (lane == 0) below = 0.f;
+        float v0 = A[0][c].x + below;
+        float v1 = A[1][c].x + A[0][c].y;
+        if (c < 4) {
+            v0 = fast_db(fmaxf(v0, 1e-10f));
+            v1 = fast_db(fmaxf(v1, 1e-10f));
+            if (2 * lane < n_mels) mx = fmaxf(mx, v0);
+            if (2 * lane + 1 < n_mels) mx = fmaxf(mx, v1);
+        }
+        if (2 * lane < n_mels) acc[(2 * lane) * C + c] = v0;
+        if (2 * lane + 1 < n_mels) acc[(2 * lane + 1) * C + c] = v1;
+    }
+    return mx;
+}
+
+#if !defined(__CUDA_ARCH__)
+// host emulation helper: phase 1 of gather_pairs (what the shuffle would see)
+template <int MODE>
+inline void gather_pairs_publish(const float2* P, const Tables& tb, int n_mels, int lane, float2* xchg) {
+    constexpr int NV = PieceGeo<MODE>::NV;
+    constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
+    const int s = 2 * lane + 1;
+    const int ps = (s < n_mels) ? tb.pb[s + 1] : 0, pe = (s < n_mels) ? tb.pb[s + 2] : 0;
+    for (int c = 0; c < NV; ++c) {
+        float2 a = make_float2(0.f, 0.f);
+        for (int j = 0; j < 3; ++j) {
+            const float2* rec = (ps + j < pe) ? P + (ps + j) * PSTRIDE : tb.zero_rec;
+            a = padd(a, rec[c]);
+        }
+        xchg[lane * NV + c] = a;
+    }
+}
+#endif
 
 // ---------------------------------------------------------------- GCC-PHAT, packed inverse transform q
 // Pair order (reference feature_extractor.py:207-208): 0:(0,1) 1:(0,2) 2:(0,3) 3:(1,2) 4:(1,3) 5:(2,3).

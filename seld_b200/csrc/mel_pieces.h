@@ -16,6 +16,7 @@ struct MelPieces {
     std::vector<int> piece0;                      // [32]
     std::vector<int> pb;                          // [n_mels + 2]
     int n_pieces = 0;
+    int max_pieces_per_seg = 0;
 };
 
 // returns "" on success, else an error message
@@ -61,6 +62,11 @@ inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, Mel
         }
     }
     out.n_pieces = int(piece_seg.size());
+    out.max_pieces_per_seg = 0;
+    for (size_t i = 0, run = 0; i < piece_seg.size(); ++i) {
+        run = (i > 0 && piece_seg[i] == piece_seg[i - 1]) ? run + 1 : 1;
+        if (int(run) > out.max_pieces_per_seg) out.max_pieces_per_seg = int(run);
+    }
     // pb[j] = first piece with seg >= j - 1   (pieces are sorted by seg)
     for (int j = 0; j < n_mels + 2; ++j) {
         int p = 0;

@@ -24,6 +24,7 @@ struct seld_plan {
     int* piece0;     // [32]
     int* pb;         // [n_mels + 2]
     int n_pieces;
+    int max_pieces_per_seg;
     int e_bytes;     // per-warp exchange / piece buffer bytes
     // extract launch geometry
     int warps_per_cta;

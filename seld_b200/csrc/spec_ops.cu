@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128) complex_spec_kernel(const float* __restri
 #pragma unroll
     for (int n2 = 0; n2 < R; ++n2) wreg[n2] = window[lane + 32 * n2];
     __syncthreads();
-    const Tables tb{nullptr, s_tw_t, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const Tables tb{nullptr, s_tw_t, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int n_pairs = (n_chan + 1) / 2;
     const long long items = (long long)n_pairs * t_raw;
     ClipSrc src{wav, n_samples, 1, n_samples};

@@ -13,7 +13,7 @@
 using namespace seld;
 
 template <int R, int MODE, int LAYOUT>
-static void run(const float* wav, int n_clips, long long L, int hop, int n_mels, const Tables& tb,
+static void run(const float* wav, int n_clips, long long L, int hop, int n_mels, const Tables& tb, bool gather3,
                 int T_out, float* out, float* clip_max) {
     using G = Geo<R>;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
@@ -40,7 +40,13 @@ static void run(const float* wav, int n_clips, long long L, int hop, int n_mels,
             for (int l = 0; l < 32; ++l) stage1_forward<R, LAYOUT>(src, 2, 3, start, wreg[l], tb, E.data(), l);
             for (int l = 0; l < 32; ++l) stage2_forward<R>(E.data(), S1.data(), l);
             for (int l = 0; l < 32; ++l) bin_phase<R, MODE>(S0.data(), S1.data(), tb, E.data(), 1e-8f, l);
-            for (int l = 0; l < 32; ++l) cmax = fmaxf(cmax, gather_phase<MODE>(E.data(), tb, acc.data(), n_mels, l));
+            if (gather3) {
+                std::vector<float2> xchg(32 * 8);
+                for (int l = 0; l < 32; ++l) gather_pairs_publish<MODE>(E.data(), tb, n_mels, l, xchg.data());
+                for (int l = 0; l < 32; ++l) cmax = fmaxf(cmax, gather_pairs<MODE>(E.data(), tb, acc.data(), n_mels, l, xchg.data()));
+            } else {
+                for (int l = 0; l < 32; ++l) cmax = fmaxf(cmax, gather_phase<MODE, 0>(E.data(), tb, acc.data(), n_mels, l));
+            }
             if (MODE == MODE_MIC) {
                 for (int l = 0; l < 32; ++l) gcc_stage1<R, 0>(S0.data(), S1.data(), E.data(), l);
                 for (int l = 0; l < 32; ++l) gcc_stage2<R, 0>(E.data(), tb, acc.data(), n_mels, l);
@@ -65,9 +71,10 @@ extern "C" int emu_extract(const float* wav, int layout, int n_clips, long long 
         for (int l = 0; l < 32; ++l) tw_t[k2 * 32 + l] = lin[(l * k2) % n_fft];
     MelPieces mp;
     if (!build_mel_pieces(mel_fb, n_fft / 2 + 1, n_mels, mp).empty()) return -2;
+    static const float2 zero_rec[8] = {};
     Tables tb{window, tw_t.data(), lin, reinterpret_cast<const float2*>(mp.w01.data()), mp.endmask.data(), mp.piece0.data(),
-              mp.pb.data()};
-#define GO3(RR, MM, LL) run<RR, MM, LL>(wav, n_clips, L, hop, n_mels, tb, T_out, out, clip_max)
+              mp.pb.data(), zero_rec};
+#define GO3(RR, MM, LL) run<RR, MM, LL>(wav, n_clips, L, hop, n_mels, tb, mp.max_pieces_per_seg <= 3 && n_mels <= 64, T_out, out, clip_max)
 #define GO(RR)                                                                   \
     if (n_fft == 32 * RR) {                                                      \
         if (mode == MODE_FOA) { if (layout == 0) GO3(RR, MODE_FOA, 0); else GO3(RR, MODE_FOA, 1); } \
