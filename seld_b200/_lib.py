@@ -81,9 +81,17 @@ def current_stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_checked_devices = set()
+
+
 def require_device():
-    """Fail loudly unless the current CUDA device is an sm_100 part."""
+    """Fail loudly unless the current CUDA device is an sm_100 part.  The driver query behind seld_device_check
+    (cudaGetDeviceProperties) costs milliseconds and contends on driver locks, so its verdict is cached per device:
+    calling it on every launch starved the GPU queue (sporadic 10x slow steps in per-launch timings)."""
     import torch
     if not torch.cuda.is_available():
         raise SeldError('seld_b200 needs a CUDA sm_100 (B200) device; none is visible and there is no CPU fallback')
-    check(load().seld_device_check(-1))
+    dev = torch.cuda.current_device()
+    if dev not in _checked_devices:
+        check(load().seld_device_check(-1))
+        _checked_devices.add(dev)

@@ -7,8 +7,10 @@
 // by L1/L2 and HBM sees every sample once.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -45,10 +47,17 @@ struct ExtractArgs {
     int e_bytes;              // per-warp exchange / piece buffer size
     int gather_unrolled;      // every mel segment has <= 3 pieces and n_mels <= 64: gather_pairs
     int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
-    long long n_super;        // super-chunks of warps_per_cta * kFramesPerWarp frames
+    int fpw;                  // frames per warp per super-chunk
+    int assign_blocked;       // 0: super-chunk sc -> CTA sc mod grid; 1: each CTA walks one contiguous range
+    int fsc;                  // frames per super-chunk (<= warps * fpw); odd => CTA start phases cover all 128 B offsets
+    long long n_super;        // super-chunks of warps_per_cta * fpw frames
 };
 
-constexpr int kFramesPerWarp = 8;
+static int frames_per_warp() {   // frames a warp handles per super-chunk (SELD_FPW overrides, for experiments)
+    const char* e = getenv("SELD_FPW");
+    const int n = e ? atoi(e) : 0;
+    return n > 0 ? n : 2;      // measured: 2 -> 11.53 ms, 4 -> 11.67, 8 -> 11.88, 16 -> 11.98 per 600 planar clips
+}
 
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 
@@ -153,8 +162,8 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
 
     if constexpr (EDGE) {
         for (long long sc = blockIdx.x; sc < a.n_super; sc += gridDim.x) {
-            const long long g0 = (sc * nwarps + warp) * kFramesPerWarp;
-            for (int i = 0; i < kFramesPerWarp; ++i) {
+            const long long g0 = sc * a.fsc + warp * a.fpw;
+            for (int i = 0; i < a.fpw && warp * a.fpw + i < a.fsc; ++i) {
                 const long long g = g0 + i;
                 if (g >= total_frames) break;
                 const int clip = int(g / a.frames_per_clip);
@@ -186,11 +195,14 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     } else {
         // Interior frames, software-pipelined over half-frames (one channel pair each): the raw samples of the NEXT
         // half-frame are requested before the current one's FFT starts, so HBM/L2 latency hides behind the arithmetic.
-        long long sc = blockIdx.x;
+        const long long sc_step = a.assign_blocked ? 1 : gridDim.x;
+        const long long per_cta = (a.n_super + gridDim.x - 1) / gridDim.x;
+        long long sc = a.assign_blocked ? blockIdx.x * per_cta : blockIdx.x;
+        const long long sc_end = a.assign_blocked ? (sc + per_cta < a.n_super ? sc + per_cta : a.n_super) : a.n_super;
         int fi = 0;
         auto frame_index = [&](long long s, int i) -> long long {       // -1 past the end
-            if (s >= a.n_super) return -1;
-            const long long g = (s * nwarps + warp) * kFramesPerWarp + i;
+            if (s >= sc_end || warp * a.fpw + i >= a.fsc) return -1;
+            const long long g = s * a.fsc + warp * a.fpw + i;
             return g < total_frames ? g : -1;
         };
         auto source_of = [&](long long g, ClipSrc& src, long long& start, int& clip, int& t) {
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
             if (pr == 0) {
                 stage1_load_raw<R, LAYOUT>(src, 2, 3, start, raw, lane);
             } else {
-                if (++fi == kFramesPerWarp) { fi = 0; sc += gridDim.x; }
+                if (++fi == a.fpw || warp * a.fpw + fi >= a.fsc) { fi = 0; sc += sc_step; }
                 g_next = frame_index(sc, fi);
             }
             const int clip_now = clip;
@@ -251,11 +263,19 @@ template <int R, int MODE, int LAYOUT, bool EDGE>
 static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream) {
     a.frames_per_clip = EDGE ? a.t_lo + (a.t_tot - a.t_hi) : a.t_hi - a.t_lo;
     if (a.frames_per_clip <= 0) return SELD_OK;
-    const long long per_super = (long long)plan->warps_per_cta * kFramesPerWarp;
+    a.fpw = frames_per_warp();
+    a.assign_blocked = 0;
+    a.fsc = plan->warps_per_cta * a.fpw;
+    const long long per_super = a.fsc;
     a.n_super = ((long long)a.n_clips * a.frames_per_clip + per_super - 1) / per_super;
     long long grid = a.n_super < plan->grid ? a.n_super : plan->grid;
-    SELD_CUDA_TRY(cudaFuncSetAttribute(extract_kernel<R, MODE, LAYOUT, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       plan->extract_smem_bytes));
+    static std::atomic<unsigned long long> configured{0};        // bit d: attribute set on device d (per instantiation)
+    const unsigned long long bit = 1ull << (plan->device & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        SELD_CUDA_TRY(cudaFuncSetAttribute(extract_kernel<R, MODE, LAYOUT, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           plan->max_smem_optin));
+        configured.fetch_or(bit, std::memory_order_release);
+    }
     extract_kernel<R, MODE, LAYOUT, EDGE><<<(int)grid, plan->warps_per_cta * 32, plan->extract_smem_bytes, stream>>>(a);
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;

@@ -149,6 +149,28 @@ SELD_HD void pfft_dif(float2* v) {
 // wreg[n2] = window[lane + 32*n2] is held in registers by the caller for the whole kernel.
 // Interior frames (whole frame inside the clip, no reflection): one 64-bit load per tap when the two channels
 // of the pair are adjacent in memory (interleaved layout, ch_b == ch_a + 1, ch_a even), else two 32-bit loads.
+// streaming-load helpers (L1 no-allocate).  Measured on B200: planar 11.8 -> 12.15 ms, interleaved 12.9 -> 15.1 ms per 600
+// clips, because the second channel pair of an interleaved frame re-reads the sectors the first pair brought into L1;
+// the hot loads therefore use plain ld.global and these stay unused.
+SELD_HD float ld_stream(const float* p) {
+#if defined(__CUDA_ARCH__)
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+SELD_HD float2 ld_stream2(const float2* p) {
+#if defined(__CUDA_ARCH__)
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+
 template <int R, int LAYOUT>
 SELD_HD void stage1_load_raw(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, float2* raw, int lane) {
     if constexpr (LAYOUT == LAYOUT_INTERLEAVED_LC) {
@@ -326,6 +348,7 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
     for (int c = 0; c < NV; ++c) acc2[c] = make_float2(0.f, 0.f);
     const float inv_eps = 1.0f / eps;
 
+    // fully unrolled: measured 12% faster than a x2-rolled loop despite the larger instruction footprint
 #pragma unroll
     for (int i = 0; i < G::BPT; ++i) {
         const bool valid = kbeg + i < G::F;

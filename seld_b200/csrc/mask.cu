@@ -158,9 +158,12 @@ extern "C" int seld_mask(void* x_dev, int dtype, int64_t n_samples, int64_t t, i
     if (freq_n > 0 && freq_max > f) { set_error("freq max_mask_size exceeds the axis length"); return SELD_EINVAL; }
     if (rng_mode == SELD_RNG_TF_EAGER_COMPAT && op_seed2_dev == nullptr) { set_error("TF_EAGER_COMPAT needs op_seed2"); return SELD_EINVAL; }
     if (rng_mode != SELD_RNG_TF_EAGER_COMPAT && rng_mode != SELD_RNG_PHILOX_COUNTER) { set_error("bad rng_mode"); return SELD_EINVAL; }
-    int dev = 0, num_sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    static const int num_sms = [] {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
     MaskArgs a;
     a.x = x_dev;
     a.n_samples = n_samples; a.t = t; a.mid = mid; a.f = f; a.c = c;

@@ -146,10 +146,13 @@ using namespace seld;
 
 extern "C" {
 
-static int sm_count() {
-    int dev = 0, n = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+static int sm_count() {          // one cheap attribute query per process (every rank drives one device)
+    static const int n = [] {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
     return n;
 }
 static int stats_block_count() { return sm_count() * 4; }

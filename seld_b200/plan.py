@@ -61,7 +61,7 @@ def get_plan(sample_rate, mode='foa', n_mels=64, pad=0, n_fft=512, win_length=No
     """Cached plan for the keyword set of reference complex_spec (feature_extractor.py:153-158); `pad` is handled
     by the caller (zero-padding the waveform)."""
     n_fft, win_length, hop_length = tables.resolve_stft(n_fft, win_length, hop_length)
-    _lib.require_device()
+    _lib.require_device()           # cached per device after the first call
     key = (int(sample_rate), n_fft, win_length, hop_length, int(n_mels), mode, bool(normalized), torch.cuda.current_device())
     with _cache_lock:
         plan = _cache.get(key)

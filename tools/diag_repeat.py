@@ -18,7 +18,8 @@ wav = torch.stack([base[i % 8] for i in range(clips)])
 if layout == 'interleaved':
     wav = wav.transpose(1, 2).contiguous()
 out = torch.empty(clips, 3000, 64, 7, device='cuda')
-smi = subprocess.Popen(['nvidia-smi', '--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.active',
+use_smi = os.environ.get('DIAG_SMI', '0') == '1'
+smi = None if not use_smi else subprocess.Popen(['nvidia-smi', '--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.active',
                         '--format=csv,noheader', '-lms', '50'], stdout=subprocess.PIPE, text=True)
 time.sleep(0.3)
 n = 40
@@ -29,8 +30,10 @@ for i in range(n):
     ev[i + 1].record()
 torch.cuda.synchronize()
 time.sleep(0.2)
-smi.terminate()
 print(layout, clips, 'ms per launch:', ' '.join(f'{ev[i].elapsed_time(ev[i + 1]):.1f}' for i in range(n)))
+if smi is None:
+    sys.exit(0)
+smi.terminate()
 lines = smi.stdout.read().strip().splitlines()
 print('smi samples:', len(lines))
 for ln in lines[::max(1, len(lines) // 12)]:
