@@ -12,46 +12,103 @@
 
 namespace seld {
 
-// ------------------------------------------------------------------ finalize
-// One thread per float4 (row length n_mels*C is a multiple of 4) or per scalar (VEC = 1).
-template <int VEC>
-__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ in, const unsigned int* __restrict__ keys,
-                                                        long long n_vec, int t_out, int t_valid, int row_len, int n_ch,
-                                                        float top_db, const float* __restrict__ mean,
-                                                        const float* __restrict__ stdv, float eps, float* __restrict__ out) {
+// ------------------------------------------------------------------ row walkers
+// Both streaming kernels use the same geometry: a block is (G4 float4 column groups) x (RP row phases); a thread owns 4
+// fixed (mel, chan) columns -- so its clamp mask, mean and 1/std live in registers -- and walks the block's contiguous row
+// slab with UNROLL independent 128-bit loads in flight.  (clip, t) advance incrementally: no division per element.
+constexpr int kUnroll = 4;
+
+struct RowCursor {
+    long long clip;
+    int t;
+    __device__ __forceinline__ void init(long long row, int t_out) { clip = row / t_out; t = int(row - clip * t_out); }
+    __device__ __forceinline__ void advance(int rows, int t_out) {
+        t += rows;
+        while (t >= t_out) { t -= t_out; ++clip; }
+    }
+};
+
+__device__ __forceinline__ float floor_of(const unsigned int* __restrict__ keys, const RowCursor& c, int t_valid, float top_db) {
+    return (keys != nullptr && c.t < t_valid) ? key_to_float(__ldg(keys + c.clip)) - top_db : -INFINITY;
+}
+
+// ------------------------------------------------------------------ finalize (vector path: row_len % 4 == 0)
+__global__ void __launch_bounds__(512) finalize_rows_kernel(const float* __restrict__ in, const unsigned int* __restrict__ keys,
+                                                            long long n_rows, int t_out, int t_valid, int row_len, int n_ch,
+                                                            float top_db, const float* __restrict__ mean,
+                                                            const float* __restrict__ stdv, float eps, int g4, int rp,
+                                                            float* __restrict__ out) {
+    const int g = threadIdx.x % g4, ph = threadIdx.x / g4;
+    const long long rows_per_block = (n_rows + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > n_rows) r1 = n_rows;
+    bool logmel[4];
+    float m[4], inv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        logmel[j] = ((4 * g + j) % n_ch) < 4;
+        m[j] = mean ? mean[4 * g + j] : 0.f;
+        inv[j] = mean ? 1.0f / fmaxf(stdv[4 * g + j], eps) : 1.f;
+    }
+    RowCursor cur;
+    cur.init(r0 + ph, t_out);
+    const float4* src = reinterpret_cast<const float4*>(in);
+    float4* dst = reinterpret_cast<float4*>(out);
+    const long long stride4 = (long long)rp * g4;             // float4 elements between a thread's consecutive rows
+    long long r = r0 + ph;
+    for (; r + (long long)(kUnroll - 1) * rp < r1; r += (long long)kUnroll * rp) {
+        float4 v[kUnroll];
+        float fl[kUnroll];
+        const long long base = r * g4 + g;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = __ldcs(src + base + u * stride4);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) { fl[u] = floor_of(keys, cur, t_valid, top_db); cur.advance(rp, t_out); }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (logmel[j]) x[j] = fmaxf(x[j], fl[u]);
+                x[j] = (x[j] - m[j]) * inv[j];
+            }
+            __stcs(dst + base + u * stride4, make_float4(x[0], x[1], x[2], x[3]));
+        }
+    }
+    for (; r < r1; r += rp) {
+        const float fl = floor_of(keys, cur, t_valid, top_db);
+        cur.advance(rp, t_out);
+        const float4 q = __ldcs(src + r * g4 + g);
+        float x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (logmel[j]) x[j] = fmaxf(x[j], fl);
+            x[j] = (x[j] - m[j]) * inv[j];
+        }
+        __stcs(dst + r * g4 + g, make_float4(x[0], x[1], x[2], x[3]));
+    }
+}
+
+// generic fallback (row_len % 4 != 0 or unaligned): one element per thread
+__global__ void __launch_bounds__(256) finalize_scalar_kernel(const float* __restrict__ in, const unsigned int* __restrict__ keys,
+                                                              long long n, int t_out, int t_valid, int row_len, int n_ch,
+                                                              float top_db, const float* __restrict__ mean,
+                                                              const float* __restrict__ stdv, float eps, float* __restrict__ out) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-        const long long e = i * VEC;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         const long long row = e / row_len;
         const int p = int(e - row * row_len);
-        const int t = int(row % t_out);
-        float floor_db = -INFINITY;
-        if (keys != nullptr && t < t_valid) floor_db = key_to_float(keys[row / t_out]) - top_db;
-        float v[VEC];
-        if constexpr (VEC == 4) {
-            const float4 q = __ldcs(reinterpret_cast<const float4*>(in) + i);
-            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        } else {
-            v[0] = in[e];
-        }
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const int c = (p + j) % n_ch;
-            if (c < 4) v[j] = fmaxf(v[j], floor_db);
-            if (mean != nullptr) v[j] = (v[j] - mean[p + j]) / fmaxf(stdv[p + j], eps);
-        }
-        if constexpr (VEC == 4) {
-            __stcs(reinterpret_cast<float4*>(out) + i, make_float4(v[0], v[1], v[2], v[3]));
-        } else {
-            out[e] = v[0];
-        }
+        float v = in[e];
+        if ((p % n_ch) < 4 && keys != nullptr && int(row % t_out) < t_valid) v = fmaxf(v, key_to_float(keys[row / t_out]) - top_db);
+        if (mean != nullptr) v = (v - mean[p]) * (1.0f / fmaxf(stdv[p], eps));
+        out[e] = v;
     }
 }
 
 // ------------------------------------------------------------------ statistics
-// Block = G4 column groups (float4 each) x RP row phases.  Each thread owns 4 fixed (mel, chan) columns and
-// walks its block's row slab; partial sums stay in float64 registers, are folded over the row phases through
-// shared memory in a fixed order, and land in partials[block][2 * row_len].
+// Partial sums stay in float64 registers, are folded over the row phases through shared memory in a fixed order, and
+// land in partials[block][2 * row_len]; stats_fold_kernel adds the blocks in block order => run-to-run deterministic.
 __global__ void __launch_bounds__(512) stats_partial_kernel(const float* __restrict__ x, const unsigned int* __restrict__ keys,
                                                             long long n_rows, int t_out, int t_valid, int row_len, int n_ch,
                                                             float top_db, int g4, int rp, double* __restrict__ partials) {
@@ -59,33 +116,49 @@ __global__ void __launch_bounds__(512) stats_partial_kernel(const float* __restr
     const int g = threadIdx.x % g4;
     const int ph = threadIdx.x / g4;
     double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-    if (ph < rp) {
-        const long long rows_per_block = (n_rows + gridDim.x - 1) / gridDim.x;
-        const long long r0 = (long long)blockIdx.x * rows_per_block;
-        long long r1 = r0 + rows_per_block;
-        if (r1 > n_rows) r1 = n_rows;
-        int cidx[4];
+    const long long rows_per_block = (n_rows + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > n_rows) r1 = n_rows;
+    bool logmel[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cidx[j] = (4 * g + j) % n_ch;
-        for (long long r = r0 + ph; r < r1; r += rp) {
-            const int t = int(r % t_out);
-            float floor_db = -INFINITY;
-            if (keys != nullptr && t < t_valid) floor_db = key_to_float(keys[r / t_out]) - top_db;
-            const float4 v4 = __ldcs(reinterpret_cast<const float4*>(x + r * row_len) + g);
-            float v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (cidx[j] < 4) v[j] = fmaxf(v[j], floor_db);
-                const double d = double(v[j]);
-                s[j] += d;
-                q[j] = fma(d, d, q[j]);
-            }
-        }
+    for (int j = 0; j < 4; ++j) logmel[j] = ((4 * g + j) % n_ch) < 4;
+    RowCursor cur;
+    cur.init(r0 + ph, t_out);
+    const float4* src = reinterpret_cast<const float4*>(x);
+    const long long stride4 = (long long)rp * g4;
+    long long r = r0 + ph;
+    auto add = [&](const float4& v4, float fl) {
+        float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            red[(size_t)ph * 2 * row_len + 4 * g + j] = s[j];
-            red[(size_t)ph * 2 * row_len + row_len + 4 * g + j] = q[j];
+            if (logmel[j]) v[j] = fmaxf(v[j], fl);
+            const double d = double(v[j]);
+            s[j] += d;
+            q[j] = fma(d, d, q[j]);
         }
+    };
+    for (; r + (long long)(kUnroll - 1) * rp < r1; r += (long long)kUnroll * rp) {
+        float4 v[kUnroll];
+        const long long base = r * g4 + g;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = __ldcs(src + base + u * stride4);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const float fl = floor_of(keys, cur, t_valid, top_db);
+            cur.advance(rp, t_out);
+            add(v[u], fl);
+        }
+    }
+    for (; r < r1; r += rp) {
+        const float fl = floor_of(keys, cur, t_valid, top_db);
+        cur.advance(rp, t_out);
+        add(__ldcs(src + r * g4 + g), fl);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        red[(size_t)ph * 2 * row_len + 4 * g + j] = s[j];
+        red[(size_t)ph * 2 * row_len + row_len + 4 * g + j] = q[j];
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * row_len; i += blockDim.x) {
@@ -167,17 +240,23 @@ int seld_finalize(int n_mels, int n_ch, const float* feat_in_dev, const uint32_t
     const long long n = (long long)n_clips * t_out * row_len;
     if (n == 0) return SELD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool vec = (row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat_in_dev) | reinterpret_cast<uintptr_t>(feat_out_dev)) % 16 == 0);
-    const long long n_vec = vec ? n / 4 : n;
-    long long blocks = (n_vec + 255) / 256;
-    const long long cap = (long long)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    if (vec)
-        finalize_kernel<4><<<(int)blocks, 256, 0, st>>>(feat_in_dev, clip_max_key_dev, n_vec, t_out, t_valid, row_len,
-                                                        n_ch, top_db, mean_dev, std_dev, eps, feat_out_dev);
-    else
-        finalize_kernel<1><<<(int)blocks, 256, 0, st>>>(feat_in_dev, clip_max_key_dev, n_vec, t_out, t_valid, row_len,
-                                                        n_ch, top_db, mean_dev, std_dev, eps, feat_out_dev);
+    const int g4 = row_len / 4;
+    const bool vec = (row_len % 4 == 0) && g4 <= 512 &&
+                     ((reinterpret_cast<uintptr_t>(feat_in_dev) | reinterpret_cast<uintptr_t>(feat_out_dev)) % 16 == 0);
+    if (vec) {
+        const long long n_rows = (long long)n_clips * t_out;
+        const int rp = 512 / g4;
+        long long blocks = (long long)sm_count() * 4;
+        if (blocks > n_rows) blocks = n_rows;
+        finalize_rows_kernel<<<(int)blocks, g4 * rp, 0, st>>>(feat_in_dev, clip_max_key_dev, n_rows, t_out, t_valid, row_len, n_ch,
+                                                              top_db, mean_dev, std_dev, eps, g4, rp, feat_out_dev);
+    } else {
+        long long blocks = (n + 255) / 256;
+        const long long cap = (long long)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        finalize_scalar_kernel<<<(int)blocks, 256, 0, st>>>(feat_in_dev, clip_max_key_dev, n, t_out, t_valid, row_len, n_ch, top_db,
+                                                            mean_dev, std_dev, eps, feat_out_dev);
+    }
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;
 }
