@@ -265,25 +265,38 @@ def main():
     if not args.no_e2e:
         ne = args.e2e_clips or (n if world == 1 else min(n, 150))
         try:
-            host_in = torch.empty(ne, 4, L, dtype=torch.float32, pin_memory=True)
             host_out = torch.empty(ne, T_OUT, N_MELS, n_ch, dtype=torch.float32, pin_memory=True)
-            host_in.copy_(wav[:ne])
+
+            def run_e2e(host_in, layout, dtype, what):
+                ex = pipeline.HostDatasetExtractor(ne, L, SR, mode=mode, n_mels=N_MELS, t_out=T_OUT, chunk_clips=24,
+                                                   layout=layout, dtype=dtype, **PROD)
+                ex.run(host_in, host_out)                                 # warm-up
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    ex.run(host_in, host_out)
+                barrier()
+                dt = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                return {'value': world * ne * CLIP_HOURS / dt.item(), 'unit': UNIT, 'h2d_bytes_per_step': ex.h2d_bytes,
+                        'd2h_bytes_per_step': ex.d2h_bytes, 'clips_per_gpu': ne, 'ms_per_step': 1000.0 * dt.item(),
+                        'host_input': what, 'api': 'seld_b200.pipeline.HostDatasetExtractor.run(pinned wav, pinned out)',
+                        'checksum': float(host_out[0, :8].double().sum())}
+
+            # (1) the reference's call surface: decoded float32 [clip, 4, L] tensors (what torchaudio.load returns)
+            host_f32 = torch.empty(ne, 4, L, dtype=torch.float32, pin_memory=True)
+            host_f32.copy_(wav[:ne])
+            # (2) the same audio as it sits in the WAV files: 16-bit PCM frames [clip, L, 4]; decoded on the GPU
+            host_pcm = torch.empty(ne, L, 4, dtype=torch.int16, pin_memory=True)
+            for c0 in range(0, ne, 50):
+                c1 = min(ne, c0 + 50)
+                host_pcm[c0:c1].copy_(torch.clamp(torch.round(wav[c0:c1].transpose(1, 2) * 32768.0), -32768, 32767).to(torch.int16))
             del wav, feat, wav_k
             torch.cuda.empty_cache()
-            ex = pipeline.HostDatasetExtractor(ne, L, SR, mode=mode, n_mels=N_MELS, t_out=T_OUT, chunk_clips=24, **PROD)
-            ex.run(host_in, host_out)                                     # warm-up
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                ex.run(host_in, host_out)
-            barrier()
-            dt = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            e2e = {'value': world * ne * CLIP_HOURS / dt.item(), 'unit': UNIT, 'h2d_bytes_per_step': ex.h2d_bytes,
-                   'd2h_bytes_per_step': ex.d2h_bytes, 'clips_per_gpu': ne, 'ms_per_step': 1000.0 * dt.item(),
-                   'api': 'seld_b200.pipeline.HostDatasetExtractor.run(pinned wav, pinned out)',
-                   'checksum': float(host_out[0, :8].double().sum())}
+            e2e = run_e2e(host_f32, 'planar', torch.float32, 'float32 [clip,4,L] (torchaudio.load layout)')
+            del host_f32
+            e2e['pcm16'] = run_e2e(host_pcm, 'interleaved', torch.int16, 'int16 PCM [clip,L,4] (WAV frame order), decoded on the GPU')
         except RuntimeError as exc:                                       # e.g. not enough pinnable host memory
             e2e = {'value': None, 'unit': UNIT, 'error': str(exc).splitlines()[0][:200]}
 

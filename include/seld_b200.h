@@ -92,6 +92,14 @@ SELD_API int64_t seld_plan_num_frames(seld_plan_t plan, int64_t n_samples);
 SELD_API int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips, int64_t n_samples, int t_out,
                  float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream);
 
+/*
+ * Same as seld_extract for 16-bit PCM input, pcm_dev[n_clips][n_samples][4] int16 -- the frame order of a WAV `data`
+ * chunk -- decoded like torchaudio.load (reference feature_extractor.py:43): sample / 32768.  Halves the input bytes
+ * (H2D and HBM) against float32; bit-identical to decoding on the host and calling seld_extract.
+ */
+SELD_API int seld_extract_pcm16(seld_plan_t plan, const int16_t* pcm_dev, int n_clips, int64_t n_samples, int t_out,
+                                float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream);
+
 SELD_API int seld_clip_max_decode(const uint32_t* clip_max_key_dev, int n_clips, float* clip_max_dev, void* stream);
 
 /*
@@ -157,6 +165,17 @@ SELD_API int seld_complex_spec(seld_plan_t plan, const float* wav_dev, int n_cha
 SELD_API int seld_foa_iv(const float* spec_dev, int64_t n, float eps, float* iv_dev, void* stream);
 SELD_API int seld_gcc(const float* spec_dev, int n_chan, int64_t n_frames, int n_bins, int n_lags, int first_lag, float* gcc_dev,
              void* stream);
+
+/*
+ * GCC-PHAT lag projection on the tensor cores (tcgen05.mma, FP16 operands, FP32 accumulation in TMEM): the pruned
+ * inverse transform of reference feature_extractor.py:210-211 as a dense contraction,
+ *     out[rows][64] = scale * A[rows][1024] * Bt[64][1024]^T
+ * A: unit phasors, row = (frame, pair), K order (Re P[0], Re P[512], Re P[1], Im P[1], ..., Re P[511], Im P[511]);
+ * Bt: the matching inverse-DFT basis (seld_b200.tables.gcc_basis).  a_dev / bt_dev are __half, 16-byte aligned.
+ * The fused MIC extractor drives the same kernel in scatter mode; this entry point exists for tests and for callers
+ * that hold their own phasors.
+ */
+SELD_API int seld_gcc_gemm(const void* a_dev, const void* bt_dev, int64_t rows, float scale, float* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     // ---- this lane's window taps stay in registers for the whole kernel
     float wreg[R];
 #pragma unroll
-    for (int n2 = 0; n2 < R; ++n2) wreg[n2] = a.window[lane + 32 * n2];
+    for (int n2 = 0; n2 < R; ++n2) wreg[n2] = a.window[lane + 32 * n2] * ((EDGE ? a.layout : LAYOUT) == LAYOUT_PCM16_LC ? (1.0f / 32768.0f) : 1.0f);
     __syncthreads();
 
     const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_piece0, s_pb, s_zero};
@@ -183,7 +183,11 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
 #pragma unroll 1
                 for (int pr = 0; pr < 2; ++pr) {
                     float2 v[R];
-                    stage1_load_reflect<R>(src, 2 * pr, 2 * pr + 1, start, wreg, v, lane);
+                    if (a.layout == LAYOUT_PCM16_LC)
+                        stage1_load_reflect_pcm16<R>(reinterpret_cast<const short*>(a.wav) + (long long)clip * 4 * a.n_samples,
+                                                     a.n_samples, pr, start, wreg, v, lane);
+                    else
+                        stage1_load_reflect<R>(src, 2 * pr, 2 * pr + 1, start, wreg, v, lane);
                     stage1_fft_store<R>(v, tb, E, lane);
                     __syncwarp();
                     stage2_forward<R>(E, pr ? S1 : S0, lane);
@@ -219,19 +223,28 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
         ClipSrc src;
         long long start = 0;
         int clip = 0, t = 0;
+        auto load_frame = [&](int pair) {           // PCM16: one load brings both pairs (issued for pair 0 only)
+            if constexpr (LAYOUT == LAYOUT_PCM16_LC) {
+                if (pair == 0)
+                    stage1_load_raw_pcm16<R>(reinterpret_cast<const short*>(a.wav) + (long long)clip * 4 * a.n_samples, start, raw, lane);
+            } else {
+                stage1_load_raw<R, LAYOUT>(src, 2 * pair, 2 * pair + 1, start, raw, lane);
+            }
+        };
         if (g >= 0) {
             source_of(g, src, start, clip, t);
-            stage1_load_raw<R, LAYOUT>(src, 0, 1, start, raw, lane);
+            load_frame(0);
         }
         int pr = 0;
 #pragma unroll 1
         while (g >= 0) {
             float2 v[R];
-            apply_window<R>(raw, wreg, v);
+            if constexpr (LAYOUT == LAYOUT_PCM16_LC) apply_window_pcm16<R>(raw, pr, wreg, v);
+            else apply_window<R>(raw, wreg, v);
             // request the next half-frame
             long long g_next = g;
             if (pr == 0) {
-                stage1_load_raw<R, LAYOUT>(src, 2, 3, start, raw, lane);
+                load_frame(1);
             } else {
                 if (++fi == a.fpw || warp * a.fpw + fi >= a.fsc) { fi = 0; sc += sc_step; }
                 g_next = frame_index(sc, fi);
@@ -240,7 +253,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
             float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
             if (pr == 1 && g_next >= 0) {
                 source_of(g_next, src, start, clip, t);
-                stage1_load_raw<R, LAYOUT>(src, 0, 1, start, raw, lane);
+                load_frame(0);
             }
             stage1_fft_store<R>(v, tb, E, lane);
             __syncwarp();
@@ -283,8 +296,10 @@ static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream)
 
 template <int R, int MODE>
 static int launch_mode(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
-    int rc = (a.layout == SELD_LAYOUT_PLANAR_CL) ? launch_one<R, MODE, LAYOUT_PLANAR_CL, false>(plan, a, stream)
-                                                 : launch_one<R, MODE, LAYOUT_INTERLEAVED_LC, false>(plan, a, stream);
+    int rc;
+    if (a.layout == LAYOUT_PLANAR_CL) rc = launch_one<R, MODE, LAYOUT_PLANAR_CL, false>(plan, a, stream);
+    else if (a.layout == LAYOUT_INTERLEAVED_LC) rc = launch_one<R, MODE, LAYOUT_INTERLEAVED_LC, false>(plan, a, stream);
+    else rc = launch_one<R, MODE, LAYOUT_PCM16_LC, false>(plan, a, stream);
     if (rc != SELD_OK) return rc;
     return launch_one<R, MODE, LAYOUT_PLANAR_CL, true>(plan, a, stream);      // edge frames: layout taken from a.layout
 }
@@ -455,10 +470,12 @@ int64_t seld_plan_num_frames(seld_plan_t plan, int64_t n_samples) {
     return 1 + n_samples / plan->hop;
 }
 
-int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips, int64_t n_samples, int t_out,
-                 float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream) {
+static int extract_common(seld_plan_t plan, const void* wav_void, int layout, int n_clips, int64_t n_samples, int t_out,
+                          float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream) {
+    const float* wav_dev = static_cast<const float*>(wav_void);
     if (!plan || !wav_dev || !feat_raw_dev || !clip_max_key_dev) { set_error("null argument"); return SELD_EINVAL; }
-    if (layout != SELD_LAYOUT_PLANAR_CL && layout != SELD_LAYOUT_INTERLEAVED_LC) { set_error("invalid layout"); return SELD_EINVAL; }
+    if (layout != LAYOUT_PLANAR_CL && layout != LAYOUT_INTERLEAVED_LC && layout != LAYOUT_PCM16_LC) { set_error("invalid layout"); return SELD_EINVAL; }
+    if (reinterpret_cast<uintptr_t>(wav_void) % 16 != 0) { set_error("wav_dev must be 16-byte aligned"); return SELD_EINVAL; }
     if (n_clips < 0 || t_out < 0) { set_error("negative size"); return SELD_EINVAL; }
     if (n_samples <= plan->n_fft / 2) {
         set_error("reflect padding needs n_fft/2 < number of samples (torch.stft raises here too)");
@@ -504,6 +521,17 @@ int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips
         case 1024: return launch_extract<32>(plan, a, st);
         default: return launch_extract<64>(plan, a, st);
     }
+}
+
+int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips, int64_t n_samples, int t_out,
+                 float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream) {
+    if (layout != SELD_LAYOUT_PLANAR_CL && layout != SELD_LAYOUT_INTERLEAVED_LC) { set_error("invalid layout"); return SELD_EINVAL; }
+    return extract_common(plan, wav_dev, layout, n_clips, n_samples, t_out, feat_raw_dev, clip_max_key_dev, stream);
+}
+
+int seld_extract_pcm16(seld_plan_t plan, const int16_t* pcm_dev, int n_clips, int64_t n_samples, int t_out,
+                       float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream) {
+    return extract_common(plan, pcm_dev, LAYOUT_PCM16_LC, n_clips, n_samples, t_out, feat_raw_dev, clip_max_key_dev, stream);
 }
 
 int seld_clip_max_decode(const uint32_t* clip_max_key_dev, int n_clips, float* clip_max_dev, void* stream) {

@@ -28,7 +28,7 @@
 namespace seld {
 
 enum { MODE_FOA = 0, MODE_MIC = 1 };
-enum { LAYOUT_PLANAR_CL = 0, LAYOUT_INTERLEAVED_LC = 1 };
+enum { LAYOUT_PLANAR_CL = 0, LAYOUT_INTERLEAVED_LC = 1, LAYOUT_PCM16_LC = 2 /* int16 [sample][4], WAV frame order */ };
 
 struct Tables {             // CTA-shared constant tables (shared memory on the device)
     const float* window;    // [N]      periodic Hann(win_length) zero-padded centred to N
@@ -182,6 +182,54 @@ SELD_HD void stage1_load_raw(const ClipSrc& src, int ch_a, int ch_b, long long f
         const float* pb = src.base + ch_b * src.chan_stride + frame_start + lane;
 #pragma unroll
         for (int n2 = 0; n2 < R; ++n2) raw[n2] = make_float2(pa[32 * n2], pb[32 * n2]);
+    }
+}
+
+// ---- 16-bit PCM input (the payload of a WAV file, 4 interleaved channels = 8 bytes per sample).  One 64-bit load per
+// tap brings all four channels, i.e. BOTH packed FFT inputs of the frame.  int16 -> float without I2F: put the 16 bits
+// (offset-binary) into the mantissa of 2^23 and subtract 2^23 + 2^15; the 1/32768 of torchaudio's decoder is folded
+// into the window taps (an exact power-of-two scaling), so the result equals window * (s / 32768) bit for bit.
+template <int R>
+SELD_HD void stage1_load_raw_pcm16(const short* base, long long frame_start, float2* raw, int lane) {
+    const float2* p = reinterpret_cast<const float2*>(base + (frame_start + lane) * 4);    // 8 bytes per sample
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2) raw[n2] = p[32 * n2];
+}
+
+SELD_HD float2 pcm16_pair_to_float(float packed) {       // two int16 in one 32-bit word -> (lo, hi) as floats
+#if defined(__CUDA_ARCH__)
+    const unsigned w = __float_as_uint(packed);
+    const unsigned lo = __byte_perm(w, 0x4B000000u, 0x7610) ^ 0x8000u;
+    const unsigned hi = __byte_perm(w, 0x4B000000u, 0x7632) ^ 0x8000u;
+    return padd(make_float2(__uint_as_float(lo), __uint_as_float(hi)), make_float2(-8421376.0f, -8421376.0f));
+#else
+    union { float f; short s[2]; } c; c.f = packed;
+    return make_float2(float(c.s[0]), float(c.s[1]));
+#endif
+}
+
+template <int R>
+SELD_HD void apply_window_pcm16(const float2* raw, int pair, const float* wreg16, float2* v) {
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2)
+        v[n2] = pmul(pcm16_pair_to_float(pair ? raw[n2].y : raw[n2].x), make_float2(wreg16[n2], wreg16[n2]));
+}
+
+// edge frames of PCM16 input (reflection): plain conversions, same value as the interior path
+template <int R>
+SELD_HD void stage1_load_reflect_pcm16(const short* base, long long n_samples, int pair, long long frame_start,
+                                       const float* wreg16, float2* v, int lane) {
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2) {
+        long long i = frame_start + lane + 32 * n2;
+        if (i < 0) i = -i;
+        if (i >= n_samples) i = 2 * (n_samples - 1) - i;
+        float a = 0.f, b = 0.f;
+        if (wreg16[n2] != 0.f) {
+            a = float(base[i * 4 + 2 * pair]);
+            b = float(base[i * 4 + 2 * pair + 1]);
+        }
+        v[n2] = make_float2(wreg16[n2] * a, wreg16[n2] * b);
     }
 }
 

@@ -24,14 +24,21 @@ def _check_cuda_f32(t, name):
         raise ValueError(f'{name} must be a contiguous float32 CUDA tensor')
 
 
-def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', out=None, **kwargs):
-    """wav: CUDA float32 [n_clips, 4, L] (layout='planar') or [n_clips, L, 4] ('interleaved').
+def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', out=None, key=None, **kwargs):
+    """wav: CUDA float32 [n_clips, 4, L] (layout='planar') or [n_clips, L, 4] ('interleaved'), or CUDA int16
+    [n_clips, L, 4] (16-bit PCM in WAV frame order, decoded as sample / 32768 like torchaudio.load).
 
     Returns (feat_raw [n_clips, t_out, n_mels, C] float32, clip_max_key [n_clips] int32 keys).  Log-mel channels
     are NOT yet clamped to clip_max - 80 dB: pass both to finalize_ / partial_statistics.
     Replaces reference feature_extractor.py:53-88 + :140-147 for a batch of clips.
     """
-    _check_cuda_f32(wav, 'wav')
+    pcm16 = isinstance(wav, torch.Tensor) and wav.dtype == torch.int16
+    if pcm16:
+        if not (wav.is_cuda and wav.is_contiguous()):
+            raise ValueError('wav must be a contiguous CUDA tensor')
+        layout = 'interleaved'                    # int16 PCM is always WAV frame order [n_clips, L, 4]
+    else:
+        _check_cuda_f32(wav, 'wav')
     if wav.dim() != 3:
         raise ValueError('wav must be [n_clips, 4, L] or [n_clips, L, 4]')
     if layout == 'planar':
@@ -45,6 +52,8 @@ def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='p
     if n_chan != 4:
         raise ValueError('the fused extractor needs exactly 4 channels')
     pad = int(kwargs.pop('pad', 0))
+    if pad > 0 and pcm16:
+        raise ValueError('pad is not supported for int16 PCM input')
     if pad > 0:   # torchaudio spectrogram(pad=...): constant zero padding of the waveform before the STFT
         dims = (pad, pad) if layout == 'planar' else (0, 0, pad, pad)
         wav = torch.nn.functional.pad(wav, dims).contiguous()
@@ -61,9 +70,14 @@ def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='p
             _check_cuda_f32(out, 'out')
             if tuple(out.shape) != shape:
                 raise ValueError(f'out must have shape {shape}')
-        key = torch.empty(n_clips, dtype=torch.int32, device=wav.device)
-        _lib.check(_lib.load().seld_extract(plan.handle, _lib.ptr(wav), code, n_clips, n_samples, int(t_out),
-                                            _lib.ptr(out), _lib.ptr(key), _lib.current_stream_ptr()))
+        if key is None:
+            key = torch.empty(n_clips, dtype=torch.int32, device=wav.device)
+        if pcm16:
+            _lib.check(_lib.load().seld_extract_pcm16(plan.handle, _lib.ptr(wav), n_clips, n_samples, int(t_out),
+                                                      _lib.ptr(out), _lib.ptr(key), _lib.current_stream_ptr()))
+        else:
+            _lib.check(_lib.load().seld_extract(plan.handle, _lib.ptr(wav), code, n_clips, n_samples, int(t_out),
+                                                _lib.ptr(out), _lib.ptr(key), _lib.current_stream_ptr()))
     return out, key
 
 
@@ -170,7 +184,7 @@ class HostDatasetExtractor:
     """
 
     def __init__(self, n_clips, n_samples, sample_rate, mode='foa', n_mels=64, t_out=None, chunk_clips=24,
-                 device=None, **kwargs):
+                 device=None, layout='planar', dtype=torch.float32, **kwargs):
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.n_clips, self.n_samples, self.sample_rate = int(n_clips), int(n_samples), sample_rate
         self.mode, self.n_mels, self.kwargs = mode, n_mels, dict(kwargs)
@@ -179,18 +193,22 @@ class HostDatasetExtractor:
             self.plan = get_plan(sample_rate, mode=mode, n_mels=n_mels, **self.kwargs)
             self.t_raw = self.plan.num_frames(n_samples)
             self.t_out = self.t_raw if t_out is None else int(t_out)
-            self.stage = [torch.empty(self.chunk, 4, n_samples, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self.layout = 'interleaved' if dtype == torch.int16 else layout
+            self.dtype = dtype
+            shape = (self.chunk, 4, n_samples) if self.layout == 'planar' else (self.chunk, n_samples, 4)
+            self.stage = [torch.empty(shape, dtype=dtype, device=self.device) for _ in range(2)]
             self.feat = torch.empty(self.n_clips, self.t_out, n_mels, self.plan.n_out_ch, dtype=torch.float32,
                                     device=self.device)
             self.key = torch.empty(self.n_clips, dtype=torch.int32, device=self.device)
             self.copy_stream = torch.cuda.Stream(device=self.device)
             self.h2d_done = [torch.cuda.Event() for _ in range(2)]
             self.stage_free = [torch.cuda.Event() for _ in range(2)]
-        self.h2d_bytes = self.n_clips * 4 * self.n_samples * 4
+        self.h2d_bytes = self.n_clips * 4 * self.n_samples * (2 if dtype == torch.int16 else 4)
         self.d2h_bytes = self.feat.numel() * 4
 
     def run(self, wav_host, out_host):
-        """wav_host: pinned float32 [n_clips, 4, L]; out_host: pinned float32 [n_clips, t_out, n_mels, C].
+        """wav_host: pinned [n_clips, 4, L] float32 (planar), [n_clips, L, 4] float32 (interleaved) or int16 (PCM);
+        out_host: pinned float32 [n_clips, t_out, n_mels, C].
         Returns (mean, std) on the device.  Synchronises before returning (the result is on the host)."""
         lib = _lib.load()
         main = torch.cuda.current_stream(self.device)
@@ -208,9 +226,8 @@ class HostDatasetExtractor:
                     self.stage[b][:n].copy_(wav_host[s:s + n], non_blocking=True)
                     self.h2d_done[b].record(self.copy_stream)
                 main.wait_event(self.h2d_done[b])
-                _lib.check(lib.seld_extract(self.plan.handle, _lib.ptr(self.stage[b]), _lib.LAYOUT_PLANAR_CL, n,
-                                            self.n_samples, self.t_out, _lib.ptr(self.feat[s:]), _lib.ptr(self.key[s:]),
-                                            _lib.current_stream_ptr()))
+                extract_batch(self.stage[b][:n], self.sample_rate, mode=self.mode, n_mels=self.n_mels, t_out=self.t_out,
+                              layout=self.layout, out=self.feat[s:s + n], key=self.key[s:s + n], **self.kwargs)
                 self.stage_free[b].record(main)
             partial_statistics(self.feat, self.key, self.t_raw, acc)
             allreduce_statistics(acc)

@@ -92,3 +92,23 @@ def test_full_size_clip_properties():
         floor = ref[..., :4].max() - 80.0
         assert abs(got[..., :4].min() - floor) <= 1e-4                  # the clamp is active on this clip
         assert (got[..., :4] <= floor + 1e-4).mean() > 0.05
+
+
+@pytest.mark.parametrize('mode', ['foa', 'mic'])
+def test_pcm16_input_is_bit_identical_to_host_decode(mode):
+    """16-bit PCM in WAV frame order [n, L, 4] (seld_extract_pcm16) == decoding on the host like torchaudio.load
+    (sample / 32768, reference feature_extractor.py:43) and extracting from float32 -- including the reflected edge
+    frames and a ragged length."""
+    from oracle import extractor as O
+    from seld_b200 import pipeline
+    from seld_b200.synth import make_clips
+    n, L = 3, 30007
+    wav = make_clips(range(70, 70 + n), L)
+    pcm = torch.clamp(torch.round(wav * 32768.0), -32768, 32767).to(torch.int16)        # [n, 4, L]
+    dec = pcm.to(torch.float32) / 32768.0
+    pcm_lc = pcm.transpose(1, 2).contiguous().cuda()                                    # [n, L, 4]
+    f16, k16 = pipeline.extract_batch(pcm_lc, 24000, mode=mode, **PROD)
+    f32, k32 = pipeline.extract_batch(dec.cuda(), 24000, mode=mode, **PROD)
+    assert torch.equal(f16, f32) and torch.equal(k16, k32)
+    pipeline.finalize_(f16, k16)
+    check_features(f16[1].cpu().numpy(), O.extract_features_port(dec[1], 24000, mode=mode, **PROD), mode, 'pcm16')
