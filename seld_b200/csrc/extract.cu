@@ -14,11 +14,26 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "extract_core.cuh"
 #include "mel_pieces.h"
 #include "plan.h"
 
 namespace seld {
+
+struct GccGemmArgs {          // gcc_gemm.cu
+    const __half* A;
+    const __half* Bt;
+    long long rows;
+    float scale;
+    float* dense_out;
+    float* feat;
+    int frames_per_clip;
+    int t_out, n_ch;
+    int blocked;
+};
+int launch_gcc_gemm(const GccGemmArgs& g, int num_sms, cudaStream_t st);
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
@@ -46,6 +61,9 @@ struct ExtractArgs {
     int hop, n_mels;
     int e_bytes;              // per-warp exchange / piece buffer size
     int gather_unrolled;      // every mel segment has <= 3 pieces and n_mels <= 64: gather_pairs
+    int gcc_tc;               // MIC: write fp16 pair phasors to gcc_rows; the tensor-core GEMM does the lag projection
+    int t_g;                  // frames per clip that have a stored row (min(t_raw, t_out))
+    float* gcc_rows;          // [n_clips * t_g * 6][512] words (fp16 re/im), A operand of gcc_gemm
     int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
     int fpw;                  // frames per warp per super-chunk
     int assign_blocked;       // 0: super-chunk sc -> CTA sc mod grid; 1: each CTA walks one contiguous range
@@ -80,7 +98,7 @@ __host__ __device__ constexpr int max_warps() { return R <= 16 ? 16 : (R == 32 ?
 
 // EDGE = false: interior frames only, loads specialised on LAYOUT (the hot kernel).
 // EDGE = true : the few frames per clip that need reflection, plus the zero padding rows (generic strided loads).
-template <int R, int MODE, int LAYOUT, bool EDGE>
+template <int R, int MODE, int LAYOUT, bool EDGE, bool TC>
 __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(ExtractArgs a) {
     using G = Geo<R>;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
@@ -128,13 +146,17 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     int run_clip = -1;
 
     // everything after the two packed FFTs of a frame: mel pieces, gather, (GCC), row store, running clip maximum
-    auto finish_frame = [&](int clip, float* row) {
-        bin_phase<R, MODE>(S0, S1, tb, E, 1e-8f, lane);
+    auto finish_frame = [&](int clip, int t, float* row) {
+        constexpr bool tc = TC && MODE == MODE_MIC && R == 32;       // tensor-core GCC: this kernel only writes phasor rows
+        bin_phase<R, MODE, tc>(S0, S1, tb, E, 1e-8f, lane);
         __syncwarp();
         float mx = a.gather_unrolled ? gather_pairs<MODE>(E, tb, acc, a.n_mels, lane)
                                      : gather_phase<MODE, 0>(E, tb, acc, a.n_mels, lane);
         __syncwarp();
-        if constexpr (MODE == MODE_MIC) {
+        if constexpr (tc) {
+            if (t < a.t_g) gcc_tc_copy_out(S0, S1, a.gcc_rows, ((long long)clip * a.t_g + t) * 6, lane);
+        }
+        if constexpr (MODE == MODE_MIC && !tc) {
             gcc_stage1<R, 0>(S0, S1, E, lane);
             __syncwarp();
             gcc_stage2<R, 0>(E, tb, acc, a.n_mels, lane);
@@ -193,7 +215,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
                     stage2_forward<R>(E, pr ? S1 : S0, lane);
                     __syncwarp();
                 }
-                finish_frame(clip, row);
+                finish_frame(clip, t, row);
             }
         }
     } else {
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
                 if (++fi == a.fpw || warp * a.fpw + fi >= a.fsc) { fi = 0; sc += sc_step; }
                 g_next = frame_index(sc, fi);
             }
-            const int clip_now = clip;
+            const int clip_now = clip, t_now = t;
             float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
             if (pr == 1 && g_next >= 0) {
                 source_of(g_next, src, start, clip, t);
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
             __syncwarp();
             stage2_forward<R>(E, pr ? S1 : S0, lane);
             __syncwarp();
-            if (pr == 1) finish_frame(clip_now, row);
+            if (pr == 1) finish_frame(clip_now, t_now, row);
             g = g_next;
             pr ^= 1;
         }
@@ -272,7 +294,7 @@ __global__ void clip_max_decode_kernel(const unsigned int* keys, int n, float* o
     if (i < n) out[i] = key_to_float(keys[i]);
 }
 
-template <int R, int MODE, int LAYOUT, bool EDGE>
+template <int R, int MODE, int LAYOUT, bool EDGE, bool TC>
 static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream) {
     a.frames_per_clip = EDGE ? a.t_lo + (a.t_tot - a.t_hi) : a.t_hi - a.t_lo;
     if (a.frames_per_clip <= 0) return SELD_OK;
@@ -285,23 +307,43 @@ static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream)
     static std::atomic<unsigned long long> configured{0};        // bit d: attribute set on device d (per instantiation)
     const unsigned long long bit = 1ull << (plan->device & 63);
     if (!(configured.load(std::memory_order_acquire) & bit)) {
-        SELD_CUDA_TRY(cudaFuncSetAttribute(extract_kernel<R, MODE, LAYOUT, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SELD_CUDA_TRY(cudaFuncSetAttribute(extract_kernel<R, MODE, LAYOUT, EDGE, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            plan->max_smem_optin));
         configured.fetch_or(bit, std::memory_order_release);
     }
-    extract_kernel<R, MODE, LAYOUT, EDGE><<<(int)grid, plan->warps_per_cta * 32, plan->extract_smem_bytes, stream>>>(a);
+    extract_kernel<R, MODE, LAYOUT, EDGE, TC><<<(int)grid, plan->warps_per_cta * 32, plan->extract_smem_bytes, stream>>>(a);
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;
 }
 
+template <int R, int MODE, bool TC>
+static int launch_kernels(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
+    int rc;
+    if (a.layout == LAYOUT_PLANAR_CL) rc = launch_one<R, MODE, LAYOUT_PLANAR_CL, false, TC>(plan, a, stream);
+    else if (a.layout == LAYOUT_INTERLEAVED_LC) rc = launch_one<R, MODE, LAYOUT_INTERLEAVED_LC, false, TC>(plan, a, stream);
+    else rc = launch_one<R, MODE, LAYOUT_PCM16_LC, false, TC>(plan, a, stream);
+    if (rc != SELD_OK) return rc;
+    return launch_one<R, MODE, LAYOUT_PLANAR_CL, true, TC>(plan, a, stream);  // edge frames: layout taken from a.layout
+}
+
 template <int R, int MODE>
 static int launch_mode(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
-    int rc;
-    if (a.layout == LAYOUT_PLANAR_CL) rc = launch_one<R, MODE, LAYOUT_PLANAR_CL, false>(plan, a, stream);
-    else if (a.layout == LAYOUT_INTERLEAVED_LC) rc = launch_one<R, MODE, LAYOUT_INTERLEAVED_LC, false>(plan, a, stream);
-    else rc = launch_one<R, MODE, LAYOUT_PCM16_LC, false>(plan, a, stream);
+    constexpr bool can_tc = (MODE == MODE_MIC && R == 32);
+    if (!(can_tc && a.gcc_tc)) return launch_kernels<R, MODE, false>(plan, a, stream);
+    int rc = launch_kernels<R, MODE, can_tc>(plan, a, stream);
     if (rc != SELD_OK) return rc;
-    return launch_one<R, MODE, LAYOUT_PLANAR_CL, true>(plan, a, stream);      // edge frames: layout taken from a.layout
+    GccGemmArgs g{};
+    g.A = reinterpret_cast<const __half*>(a.gcc_rows);
+    g.Bt = reinterpret_cast<const __half*>(plan->gcc_bt);
+    g.rows = (long long)a.n_clips * a.t_g * 6;
+    g.scale = 1.0f / 512.0f;
+    g.dense_out = nullptr;
+    g.feat = a.out;
+    g.frames_per_clip = a.t_g;
+    g.t_out = a.t_out;
+    g.n_ch = 10;
+    g.blocked = 1;
+    return launch_gcc_gemm(g, plan->num_sms, stream);
 }
 
 template <int R>
@@ -434,6 +476,26 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
         seld_plan_destroy(plan);
         return cuda_fail(e, "plan table upload");
     }
+    if (e == cudaSuccess && mode == SELD_MODE_MIC && n_fft == 1024 && n_mels == 64) {
+        // B^T of the tensor-core lag projection: [64 lags][1024] fp16, x512 (see gcc_gemm.cu / seld_b200.tables.gcc_basis)
+        std::vector<__half> bt((size_t)64 * 1024);
+        const double two_pi = 2.0 * 3.14159265358979323846264338327950288;
+        for (int j = 0; j < 64; ++j) {
+            const int lag = j - 32;
+            bt[(size_t)j * 1024 + 0] = __float2half(float(512.0 / 1024.0));
+            bt[(size_t)j * 1024 + 1] = __float2half(float(((lag & 1) ? -512.0 : 512.0) / 1024.0));
+            for (int k = 1; k < 512; ++k) {
+                const double ang = two_pi * double(k) * double(lag) / 1024.0;
+                bt[(size_t)j * 1024 + 2 * k] = __float2half(float(cos(ang)));              // 512 * 2 cos / 1024
+                bt[(size_t)j * 1024 + 2 * k + 1] = __float2half(float(-sin(ang)));
+            }
+        }
+        up((void**)&plan->gcc_bt, bt.data(), sizeof(__half) * bt.size());
+    }
+    if (e != cudaSuccess) {
+        seld_plan_destroy(plan);
+        return cuda_fail(e, "gcc basis upload");
+    }
     switch (n_fft) {
         case 256: plan_geometry<8>(plan); break;
         case 512: plan_geometry<16>(plan); break;
@@ -459,6 +521,7 @@ int seld_plan_destroy(seld_plan_t plan) {
     cudaFree(plan->endmask);
     cudaFree(plan->piece0);
     cudaFree(plan->pb);
+    cudaFree(plan->gcc_bt);
     delete plan;
     return SELD_OK;
 }
@@ -470,8 +533,17 @@ int64_t seld_plan_num_frames(seld_plan_t plan, int64_t n_samples) {
     return 1 + n_samples / plan->hop;
 }
 
+static int64_t workspace_bytes_for(const seld_plan* plan, int n_clips, int64_t n_samples, int t_out) {
+    if (!plan || plan->gcc_bt == nullptr || n_clips <= 0 || n_samples <= 0 || t_out <= 0) return 0;
+    const int64_t t_raw = 1 + n_samples / plan->hop;
+    const int64_t t_g = t_raw < t_out ? t_raw : t_out;
+    const int64_t rows = (int64_t)n_clips * t_g * 6;    // one 2 KB fp16 row per (frame, pair), in whole 128-row tiles
+    return ((rows + 127) / 128) * 128 * 2048;
+}
+
 static int extract_common(seld_plan_t plan, const void* wav_void, int layout, int n_clips, int64_t n_samples, int t_out,
-                          float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream) {
+                          float* feat_raw_dev, uint32_t* clip_max_key_dev, void* workspace_dev, int64_t workspace_bytes,
+                          void* stream) {
     const float* wav_dev = static_cast<const float*>(wav_void);
     if (!plan || !wav_dev || !feat_raw_dev || !clip_max_key_dev) { set_error("null argument"); return SELD_EINVAL; }
     if (layout != LAYOUT_PLANAR_CL && layout != LAYOUT_INTERLEAVED_LC && layout != LAYOUT_PCM16_LC) { set_error("invalid layout"); return SELD_EINVAL; }
@@ -501,6 +573,13 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
     a.piece0 = plan->piece0;
     a.pb = plan->pb;
     a.e_bytes = plan->e_bytes;
+    a.t_g = a.t_raw < t_out ? a.t_raw : t_out;
+    {
+        const int64_t need = workspace_bytes_for(plan, n_clips, n_samples, t_out);
+        a.gcc_tc = (need > 0 && workspace_dev != nullptr && workspace_bytes >= need &&
+                    reinterpret_cast<uintptr_t>(workspace_dev) % 16 == 0) ? 1 : 0;
+        a.gcc_rows = static_cast<float*>(workspace_dev);
+    }
     a.gather_unrolled = plan->max_pieces_per_seg <= 3 && plan->n_mels <= 64;
     // frames [t_lo, t_hi) need no reflection: t*hop - n_fft/2 >= 0 and t*hop + n_fft/2 <= n_samples
     {
@@ -523,15 +602,22 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
     }
 }
 
+int64_t seld_extract_workspace_bytes(seld_plan_t plan, int n_clips, int64_t n_samples, int t_out) {
+    return workspace_bytes_for(plan, n_clips, n_samples, t_out);
+}
+
 int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips, int64_t n_samples, int t_out,
-                 float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream) {
+                 float* feat_raw_dev, uint32_t* clip_max_key_dev, void* workspace_dev, int64_t workspace_bytes, void* stream) {
     if (layout != SELD_LAYOUT_PLANAR_CL && layout != SELD_LAYOUT_INTERLEAVED_LC) { set_error("invalid layout"); return SELD_EINVAL; }
-    return extract_common(plan, wav_dev, layout, n_clips, n_samples, t_out, feat_raw_dev, clip_max_key_dev, stream);
+    return extract_common(plan, wav_dev, layout, n_clips, n_samples, t_out, feat_raw_dev, clip_max_key_dev, workspace_dev,
+                          workspace_bytes, stream);
 }
 
 int seld_extract_pcm16(seld_plan_t plan, const int16_t* pcm_dev, int n_clips, int64_t n_samples, int t_out,
-                       float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream) {
-    return extract_common(plan, pcm_dev, LAYOUT_PCM16_LC, n_clips, n_samples, t_out, feat_raw_dev, clip_max_key_dev, stream);
+                       float* feat_raw_dev, uint32_t* clip_max_key_dev, void* workspace_dev, int64_t workspace_bytes,
+                       void* stream) {
+    return extract_common(plan, pcm_dev, LAYOUT_PCM16_LC, n_clips, n_samples, t_out, feat_raw_dev, clip_max_key_dev,
+                          workspace_dev, workspace_bytes, stream);
 }
 
 int seld_clip_max_decode(const uint32_t* clip_max_key_dev, int n_clips, float* clip_max_dev, void* stream) {

@@ -24,6 +24,9 @@
 #pragma once
 
 #include "seld_common.cuh"
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 namespace seld {
 
@@ -313,6 +316,16 @@ SELD_HD void stage2_forward(const float2* E, float2* S, int lane) {
     }
 }
 
+SELD_HD float rsqrt_ftz(float s) {      // one MUFU.RSQ; subnormal inputs flush to 0 -> +inf (callers clamp)
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    return r;
+#else
+    return (s < 1.17549435e-38f) ? INFINITY : 1.0f / sqrtf(s);
+#endif
+}
+
 SELD_HD float2 unit_phasor(float2 a) {   // a / |a|, (0,0) for a == 0; scaled so |a|^2 neither under- nor overflows
     float m = fmaxf(fabsf(a.x), fabsf(a.y));
     if (!(m > 0.f)) return make_float2(0.f, 0.f);
@@ -342,15 +355,6 @@ struct PieceGeo {
     static constexpr int PSTRIDE = (MODE == MODE_FOA) ? 7 : 5;      // float2 per piece record
 };
 
-SELD_HD float rsqrt_ftz(float s) {      // one MUFU.RSQ; subnormal inputs flush to 0 -> +inf (callers clamp)
-#if defined(__CUDA_ARCH__)
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
-    return r;
-#else
-    return (s < 1.17549435e-38f) ? INFINITY : 1.0f / sqrtf(s);
-#endif
-}
 
 // if (flag) rec[c] = acc[c] for c < NV (predicated stores, no branch); then acc[c] *= (flag ? 0 : 1)
 template <int NV>
@@ -382,7 +386,39 @@ SELD_HD void piece_flush(float2* acc, float2* rec, unsigned flag) {
 #endif
 }
 
-template <int R, int MODE>
+SELD_HD float2 pair_phasor(float2 um, float2 un) {   // exp(i angle(conj(Xm) Xn)); angle(0) = 0 -> 1
+    const bool zm = (um.x == 0.f && um.y == 0.f), zn = (un.x == 0.f && un.y == 0.f);
+    if (zm || zn) return make_float2(1.f, 0.f);
+    return make_float2(um.x * un.x + um.y * un.y, um.x * un.y - um.y * un.x);
+}
+
+// exp(i angle(conj(a) b)) = R / |R| with R = conj(a) b, and 1 for R == 0 (angle(0) = 0), in packed arithmetic.
+// |R|^2 below the smallest normal float flushes to 0 -> 1 (spectra under ~3e-10 of full scale; never reached by 16-bit
+// audio, whose smallest non-zero bin is ~1e-5).
+SELD_HD float2 cross_phasor(float2 a, float2 b) {
+    const float2 t = pmul(make_float2(a.x, a.x), b);                              // (ax bx, ax by)
+    const float2 r = pfma(make_float2(a.y, -a.y), make_float2(b.y, b.x), t);      // (ax bx + ay by, ax by - ay bx)
+    const float2 q = pmul(r, r);
+    const float n2 = q.x + q.y;
+    const float inv = rsqrt_ftz(n2);
+    const float2 p = pmul(r, make_float2(inv, inv));
+    return (n2 >= 1.17549435e-38f) ? p : make_float2(1.f, 0.f);
+}
+
+SELD_HD float pack_half2(float lo, float hi) {          // two floats -> one 32-bit word of two fp16 (round to nearest)
+#if defined(__CUDA_ARCH__)
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return __uint_as_float(*reinterpret_cast<const unsigned*>(&h));
+#else
+    (void)lo; (void)hi;
+    return 0.f;                                          // the tensor-core GCC path is device-only
+#endif
+}
+
+// GCC_TC (MIC only): instead of per-channel unit phasors for the CUDA-core inverse transforms, write the six PAIR
+// phasors exp(i angle(conj(X_m) X_n)) as fp16 (re, im) words into the bin's own four spectrum slots -- the A operand
+// rows of the tensor-core lag projection (gcc_gemm.cu), copied out by gcc_tc_copy_out.
+template <int R, int MODE, bool GCC_TC = false>
 SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, float eps, int lane) {
     using G = Geo<R>;
     constexpr int N = G::N;
@@ -422,7 +458,18 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
             val[5] = iy * inv4;
             val[6] = iz * inv4;
         } else {
-            if (valid) {
+            if (valid && GCC_TC) {
+                const float2 p01 = cross_phasor(ch[0], ch[1]), p02 = cross_phasor(ch[0], ch[2]), p03 = cross_phasor(ch[0], ch[3]);
+                const float2 p12 = cross_phasor(ch[1], ch[2]), p13 = cross_phasor(ch[1], ch[3]), p23 = cross_phasor(ch[2], ch[3]);
+                if (k == 0 || k == N / 2) {          // real bins: six real parts as three half2 words
+                    S0[k] = make_float2(pack_half2(p01.x, p02.x), pack_half2(p03.x, p12.x));
+                    S1[k] = make_float2(pack_half2(p13.x, p23.x), 0.f);
+                } else {
+                    S0[k] = make_float2(pack_half2(p01.x, p01.y), pack_half2(p02.x, p02.y));
+                    S0[kn] = make_float2(pack_half2(p03.x, p03.y), pack_half2(p12.x, p12.y));
+                    S1[k] = make_float2(pack_half2(p13.x, p13.y), pack_half2(p23.x, p23.y));
+                }
+            } else if (valid) {
                 const float2 u0 = unit_phasor(ch[0]), u1 = unit_phasor(ch[1]);
                 const float2 u2 = unit_phasor(ch[2]), u3 = unit_phasor(ch[3]);
                 if (k == 0 || k == N / 2) {          // real bins: both channels of a pair share one slot
@@ -573,14 +620,43 @@ inline void gather_pairs_publish(const float2* P, const Tables& tb, int n_mels, 
 }
 #endif
 
+// ---------------------------------------------------------------- tensor-core GCC: copy the A rows out
+// rows: [6][512] 32-bit words (one fp16 (re, im) pair per bin; word 0 = (Re P[0], Re P[N/2])).  Lane l copies bins
+// l, l+32, ...: coalesced 128-byte stores.  N = 1024 only.
+#if defined(__CUDACC__)
+// Destination layout = what gcc_gemm.cu reads with fully contiguous 16 KB copies: [tile][chunk][128 rows][32 words],
+// row = first_row + pair, tile = row / 128, chunk = bin / 32.
+__device__ __forceinline__ void gcc_tc_copy_out(const float2* S0, const float2* S1, float* scratch, long long first_row,
+                                                int lane) {
+    constexpr int N = 1024;
+#pragma unroll
+    for (int pp = 0; pp < 3; ++pp) {                 // slot pp holds pairs 2pp (.x) and 2pp + 1 (.y)
+        const long long ra = first_row + 2 * pp, rb = ra + 1;
+        float* dst0 = scratch + ((ra >> 7) * 16 * 128 + (ra & 127)) * 32 + lane;
+        float* dst1 = scratch + ((rb >> 7) * 16 * 128 + (rb & 127)) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {               // i = chunk; this lane's bin k = lane + 32 i
+            const int k = lane + 32 * i;
+            float2 w;
+            if (i == 0 && lane == 0) {
+                // halves 2pp, 2pp+1 of the DC triple and of the Nyquist triple -> words (Re P[0], Re P[512])
+                const unsigned dw = __float_as_uint(pp == 0 ? S0[0].x : (pp == 1 ? S0[0].y : S1[0].x));
+                const unsigned nw = __float_as_uint(pp == 0 ? S0[N / 2].x : (pp == 1 ? S0[N / 2].y : S1[N / 2].x));
+                w.x = __uint_as_float((dw & 0xffffu) | (nw << 16));
+                w.y = __uint_as_float((dw >> 16) | (nw & 0xffff0000u));
+            } else {
+                w = (pp == 0) ? S0[k] : (pp == 1 ? S0[N - k] : S1[k]);
+            }
+            dst0[i * 128 * 32] = w.x;
+            dst1[i * 128 * 32] = w.y;
+        }
+    }
+}
+#endif
+
 // ---------------------------------------------------------------- GCC-PHAT, packed inverse transform q
 // Pair order (reference feature_extractor.py:207-208): 0:(0,1) 1:(0,2) 2:(0,3) 3:(1,2) 4:(1,3) 5:(2,3).
 // Transform q carries pairs 2q (real part of the result) and 2q+1 (imaginary part).
-SELD_HD float2 pair_phasor(float2 um, float2 un) {   // exp(i angle(conj(Xm) Xn)); angle(0) = 0 -> 1
-    const bool zm = (um.x == 0.f && um.y == 0.f), zn = (un.x == 0.f && un.y == 0.f);
-    if (zm || zn) return make_float2(1.f, 0.f);
-    return make_float2(um.x * un.x + um.y * un.y, um.x * un.y - um.y * un.x);
-}
 
 template <int R, int Q>
 SELD_HD void gcc_stage1(const float2* S0, const float2* S1, float2* E, int lane) {

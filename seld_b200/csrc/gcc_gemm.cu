@@ -11,7 +11,7 @@
 //
 // Kernel: one CTA = 128 threads owns M = 128 rows at a time.  K is walked in 16 chunks of 64; each chunk of A (128 x 64
 // halfs = 16 KB, read from the phasor scratch rows the extractor wrote) and of B^T (64 x 64 halfs = 8 KB, L2 resident)
-// is brought into shared memory with 16-byte cp.async in the canonical no-swizzle K-major core-matrix layout, three
+// is brought into shared memory with coalesced 16-byte cp.async in a (padded) no-swizzle K-major core-matrix layout, three
 // stages deep; one elected thread issues 4 x tcgen05.mma (M128 N64 K16, kind::f16) per chunk accumulating in 64 TMEM
 // columns, and tcgen05.commit on the stage's mbarrier tells the loaders when the stage may be overwritten.  The epilogue
 // reads the accumulator with tcgen05.ld (warp w owns TMEM lanes 32w..32w+31 = its 32 rows), scales, and scatters the 64
@@ -28,9 +28,16 @@ constexpr int GM = 128;          // rows per tile
 constexpr int GN = 64;           // lags
 constexpr int GK = 1024;         // contraction length
 constexpr int GKC = 64;          // K elements per chunk (128 bytes per row)
-constexpr int GSTAGES = 3;
-constexpr int GA_BYTES = GM * GKC * 2;       // 16 KB
-constexpr int GB_BYTES = GN * GKC * 2;       // 8 KB
+constexpr int GSTAGES = 4;          // chunks in flight: GSTAGES - 1 ahead of the MMA
+// Shared-memory operand layout (K-major, no swizzle): element (row r, k) of a stage lives at
+//     (r / 8) * GSBO + (k / 8) * GLBO + (r % 8) * 16 + (k % 8) * 2
+// i.e. 8-row x 16-byte core matrices, K-adjacent core matrices GLBO = 144 bytes apart (128 + 16 bytes of padding) and
+// 8-row groups GSBO = 8 * 144 bytes apart.  The padding makes the coalesced global->shared copy (8 consecutive lanes =
+// the 8 k-groups of one row) hit 8 different 16-byte bank groups instead of one.
+constexpr int GLBO = 144;
+constexpr int GSBO = 8 * GLBO;               // 1152
+constexpr int GA_BYTES = (GM / 8) * GSBO;    // 18 KB
+constexpr int GB_BYTES = (GN / 8) * GSBO;    // 9 KB
 constexpr int GSTAGE_BYTES = GA_BYTES + GB_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -66,7 +73,7 @@ __device__ __forceinline__ unsigned long long umma_desc(uint32_t saddr, uint32_t
 // kind::f16 instruction descriptor: F32 accumulate, F16 x F16, both K-major, N = 64, M = 128 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t kIdesc = (1u << 4) | ((GN >> 3) << 17) | ((GM >> 4) << 24);
 
-struct GccGemmArgs {
+struct GccGemmArgs {          // (also declared in extract.cu, which drives the kernel in scatter mode)
     const __half* A;          // [rows][1024]
     const __half* Bt;         // [64][1024]   (lag-major: K contiguous)
     long long rows;
@@ -75,6 +82,7 @@ struct GccGemmArgs {
     float* feat;              // production: feature tensor [clip][t_out][64][n_ch]
     int frames_per_clip;      // rows are ((clip * frames_per_clip + t) * 6 + pair)
     int t_out, n_ch;
+    int blocked;              // A layout: 0 = row-major [rows][1024]; 1 = tile-blocked [tile][chunk][128 rows][64] (fused path)
 };
 
 __global__ void __launch_bounds__(128) gcc_gemm_kernel(GccGemmArgs g) {
@@ -97,43 +105,58 @@ __global__ void __launch_bounds__(128) gcc_gemm_kernel(GccGemmArgs g) {
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = s_tmem;
 
-    uint32_t commits[GSTAGES] = {0, 0, 0};        // tcgen05.commit count per stage barrier (uniform across threads)
+    uint32_t commits[GSTAGES] = {};        // tcgen05.commit count per stage barrier (uniform across threads)
     const long long n_tiles = (g.rows + GM - 1) / GM;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // this thread's A row (clamped past the end: duplicates are computed and discarded) and B^T row
-        long long arow = tile * GM + tid;
-        if (arow >= g.rows) arow = g.rows - 1;
-        const __half* asrc = g.A + arow * GK;
-        const __half* bsrc = g.Bt + (long long)(tid & 63) * GK;
-        const uint32_t a_off = (tid >> 3) * 1024 + (tid & 7) * 16;          // row tid inside the stage's A block
-        const uint32_t b_off = GA_BYTES + ((tid & 63) >> 3) * 1024 + (tid & 7) * 16;
+        // Coalesced copies: 8 consecutive threads fetch the 8 16-byte k-groups (one 128-byte line) of one row; a pass of
+        // the 128 threads covers 16 rows, so A takes 8 passes and B^T 4.  Rows past the end are clamped (their results
+        // are computed and discarded).
+        const int gk = tid & 7, r0 = tid >> 3;
+        const long long tile_row0 = tile * GM;
 
         auto load_chunk = [&](int c) {
             const int s = c % GSTAGES;
             const uint32_t sb = base + s * GSTAGE_BYTES;
 #pragma unroll
-            for (int gk = 0; gk < 8; ++gk) cp_async16(sb + a_off + gk * 128, asrc + c * GKC + gk * 8);
-            if (tid < 64) {
+            for (int i = 0; i < GM / 16; ++i) {
+                const int r = r0 + 16 * i;
+                const __half* src;
+                if (g.blocked) {
+                    // the extractor wrote this (tile, chunk) as one contiguous 16 KB block: full DRAM pages, and rows past
+                    // the end exist as (uninitialised, discarded) padding
+                    src = g.A + ((tile * (GK / GKC) + c) * GM + r) * GKC + gk * 8;
+                } else {
+                    long long grow = tile_row0 + r;
+                    if (grow >= g.rows) grow = g.rows - 1;
+                    src = g.A + grow * GK + c * GKC + gk * 8;
+                }
+                cp_async16(sb + (r >> 3) * GSBO + gk * GLBO + (r & 7) * 16, src);
+            }
 #pragma unroll
-                for (int gk = 0; gk < 8; ++gk) cp_async16(sb + b_off + gk * 128, bsrc + c * GKC + gk * 8);
+            for (int i = 0; i < GN / 16; ++i) {
+                const int r = r0 + 16 * i;
+                cp_async16(sb + GA_BYTES + (r >> 3) * GSBO + gk * GLBO + (r & 7) * 16, g.Bt + (long long)r * GK + c * GKC + gk * 8);
             }
         };
 
-        load_chunk(0);
-        asm volatile("cp.async.commit_group;");
-        load_chunk(1);
-        asm volatile("cp.async.commit_group;");
         constexpr int NCHUNK = GK / GKC;
+        constexpr int AHEAD = GSTAGES - 1;
+        // prologue: the previous tile's MMAs have all retired (its last commit was awaited), so every stage is free
+#pragma unroll
+        for (int c = 0; c < AHEAD; ++c) {
+            load_chunk(c);
+            asm volatile("cp.async.commit_group;");
+        }
         for (int c = 0; c < NCHUNK; ++c) {
-            if (c + 2 < NCHUNK) {
-                const int s2 = (c + 2) % GSTAGES;
+            if (c + AHEAD < NCHUNK) {
+                const int s2 = (c + AHEAD) % GSTAGES;
                 // the stage is free once the MMAs of its previous user (chunk c-1, or the previous tile) have completed
                 if (commits[s2] > 0) mbar_wait(smem_u32(&s_bar[s2]), (commits[s2] - 1) & 1);
-                load_chunk(c + 2);
+                load_chunk(c + AHEAD);
             }
             asm volatile("cp.async.commit_group;");
-            asm volatile("cp.async.wait_group 2;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD) : "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA
             __syncthreads();
             const int s = c % GSTAGES;
@@ -142,8 +165,8 @@ __global__ void __launch_bounds__(128) gcc_gemm_kernel(GccGemmArgs g) {
                 const uint32_t sa = base + s * GSTAGE_BYTES, sbb = sa + GA_BYTES;
 #pragma unroll
                 for (int j = 0; j < GKC / 16; ++j) {
-                    const unsigned long long da = umma_desc(sa + j * 256, 128, 1024);
-                    const unsigned long long db = umma_desc(sbb + j * 256, 128, 1024);
+                    const unsigned long long da = umma_desc(sa + j * 2 * GLBO, GLBO, GSBO);
+                    const unsigned long long db = umma_desc(sbb + j * 2 * GLBO, GLBO, GSBO);
                     const uint32_t accum = (c > 0 || j > 0) ? 1u : 0u;
                     asm volatile(
                         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -211,14 +234,14 @@ __global__ void __launch_bounds__(128) gcc_gemm_kernel(GccGemmArgs g) {
 
 int launch_gcc_gemm(const GccGemmArgs& g, int num_sms, cudaStream_t st) {
     if (g.rows <= 0) return SELD_OK;
-    const int smem = GSTAGES * GSTAGE_BYTES + 128;  // 72 KB -> up to 3 CTAs per SM (64 TMEM columns each)
+    const int smem = GSTAGES * GSTAGE_BYTES + 128;  // 108 KB -> 2 CTAs per SM (64 TMEM columns each)
     static std::atomic<int> configured{0};
     if (!configured.load(std::memory_order_acquire)) {
         SELD_CUDA_TRY(cudaFuncSetAttribute(gcc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured.store(1, std::memory_order_release);
     }
     const long long n_tiles = (g.rows + GM - 1) / GM;
-    long long grid = (long long)num_sms * 3;
+    long long grid = (long long)num_sms * 2;
     if (grid > n_tiles) grid = n_tiles;
     gcc_gemm_kernel<<<(int)grid, 128, smem, st>>>(g);
     SELD_CUDA_TRY(cudaGetLastError());
@@ -255,5 +278,6 @@ extern "C" int seld_gcc_gemm(const void* a_dev, const void* bt_dev, int64_t rows
     g.frames_per_clip = 1;
     g.t_out = 1;
     g.n_ch = 10;
+    g.blocked = 0;
     return launch_gcc_gemm(g, sms, static_cast<cudaStream_t>(stream));
 }

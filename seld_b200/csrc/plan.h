@@ -23,6 +23,7 @@ struct seld_plan {
     unsigned long long* endmask;  // [32]
     int* piece0;     // [32]
     int* pb;         // [n_mels + 2]
+    void* gcc_bt;    // MIC, n_fft 1024, 64 lags: fp16 [64][1024] basis of the tensor-core lag projection (else null)
     int n_pieces;
     int max_pieces_per_seg;
     int e_bytes;     // per-warp exchange / piece buffer bytes

@@ -24,7 +24,21 @@ def _check_cuda_f32(t, name):
         raise ValueError(f'{name} must be a contiguous float32 CUDA tensor')
 
 
-def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', out=None, key=None, **kwargs):
+_workspaces = {}
+
+
+def _workspace(device, n_bytes):
+    """Per-device scratch for the tensor-core GCC path, grown on demand (stream-ordered reuse: every use is enqueued
+    on the current stream before the next one)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < n_bytes:
+        _workspaces[key] = buf = torch.empty(n_bytes, dtype=torch.uint8, device=device)
+    return buf
+
+
+def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', out=None, key=None,
+                  use_tensor_cores=True, **kwargs):
     """wav: CUDA float32 [n_clips, 4, L] (layout='planar') or [n_clips, L, 4] ('interleaved'), or CUDA int16
     [n_clips, L, 4] (16-bit PCM in WAV frame order, decoded as sample / 32768 like torchaudio.load).
 
@@ -72,12 +86,18 @@ def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='p
                 raise ValueError(f'out must have shape {shape}')
         if key is None:
             key = torch.empty(n_clips, dtype=torch.int32, device=wav.device)
+        lib = _lib.load()
+        ws, ws_bytes = None, 0
+        if use_tensor_cores:
+            ws_bytes = int(lib.seld_extract_workspace_bytes(plan.handle, n_clips, n_samples, int(t_out)))
+            if ws_bytes > 0:
+                ws = _workspace(wav.device, ws_bytes)
         if pcm16:
-            _lib.check(_lib.load().seld_extract_pcm16(plan.handle, _lib.ptr(wav), n_clips, n_samples, int(t_out),
-                                                      _lib.ptr(out), _lib.ptr(key), _lib.current_stream_ptr()))
+            _lib.check(lib.seld_extract_pcm16(plan.handle, _lib.ptr(wav), n_clips, n_samples, int(t_out),
+                                              _lib.ptr(out), _lib.ptr(key), _lib.ptr(ws), ws_bytes, _lib.current_stream_ptr()))
         else:
-            _lib.check(_lib.load().seld_extract(plan.handle, _lib.ptr(wav), code, n_clips, n_samples, int(t_out),
-                                                _lib.ptr(out), _lib.ptr(key), _lib.current_stream_ptr()))
+            _lib.check(lib.seld_extract(plan.handle, _lib.ptr(wav), code, n_clips, n_samples, int(t_out),
+                                        _lib.ptr(out), _lib.ptr(key), _lib.ptr(ws), ws_bytes, _lib.current_stream_ptr()))
     return out, key
 
 

@@ -112,3 +112,16 @@ def test_pcm16_input_is_bit_identical_to_host_decode(mode):
     assert torch.equal(f16, f32) and torch.equal(k16, k32)
     pipeline.finalize_(f16, k16)
     check_features(f16[1].cpu().numpy(), O.extract_features_port(dec[1], 24000, mode=mode, **PROD), mode, 'pcm16')
+
+
+def test_mic_tensor_core_gcc_matches_cuda_core_path():
+    """MIC, production geometry: the tcgen05 lag projection (fp16 operands) vs the pruned inverse FFT on CUDA cores."""
+    from seld_b200 import pipeline
+    from seld_b200.synth import make_clips
+    wav = make_clips(range(20, 24), 40000).cuda()
+    for t_out in (None, 70, 90):
+        a, ka = pipeline.extract_batch(wav, 24000, mode='mic', t_out=t_out, use_tensor_cores=True, **PROD)
+        b, kb = pipeline.extract_batch(wav, 24000, mode='mic', t_out=t_out, use_tensor_cores=False, **PROD)
+        assert torch.equal(ka, kb) and torch.equal(a[..., :4], b[..., :4])          # log-mel part is the same code
+        err = float((a[..., 4:] - b[..., 4:]).abs().max())
+        assert err <= 3e-4, err
