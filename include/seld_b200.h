@@ -178,13 +178,16 @@ SELD_API int seld_gcc(const float* spec_dev, int n_chan, int64_t n_frames, int n
 /*
  * GCC-PHAT lag projection on the tensor cores (tcgen05.mma, FP16 operands, FP32 accumulation in TMEM): the pruned
  * inverse transform of reference feature_extractor.py:210-211 as a dense contraction,
- *     out[rows][64] = scale * A[rows][1024] * Bt[64][1024]^T
+ *     out[rows][64] = scale * A[rows][1024] * B[1024][64]
  * A: unit phasors, row = (frame, pair), K order (Re P[0], Re P[512], Re P[1], Im P[1], ..., Re P[511], Im P[511]);
- * Bt: the matching inverse-DFT basis (seld_b200.tables.gcc_basis).  a_dev / bt_dev are __half, 16-byte aligned.
- * The fused MIC extractor drives the same kernel in scatter mode; this entry point exists for tests and for callers
- * that hold their own phasors.
+ * B: the matching inverse-DFT basis (seld_b200.tables.gcc_basis).  Both operands are passed as UMMA operand IMAGES
+ * (seld_b200.tables.gcc_operand_image): a_img_dev [ceil(rows/128)][16 chunks][16 KB], bt_img_dev [16 chunks][8 KB],
+ * __half, 16-byte aligned -- the layout the kernel bulk-copies straight into shared memory.  The fused MIC extractor
+ * writes that image itself and drives the same kernel with an epilogue that assembles complete feature rows; this
+ * entry point exists for tests and for callers that hold their own phasors.
  */
-SELD_API int seld_gcc_gemm(const void* a_dev, const void* bt_dev, int64_t rows, float scale, float* out_dev, void* stream);
+SELD_API int seld_gcc_gemm(const void* a_img_dev, const void* bt_img_dev, int64_t rows, float scale, float* out_dev,
+                           void* stream);
 
 #ifdef __cplusplus
 }

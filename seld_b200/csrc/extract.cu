@@ -25,13 +25,14 @@ namespace seld {
 struct GccGemmArgs {          // gcc_gemm.cu
     const __half* A;
     const __half* Bt;
-    long long rows;
+    long long n_tiles;
     float scale;
     float* dense_out;
+    long long dense_rows;
     float* feat;
-    int frames_per_clip;
-    int t_out, n_ch;
-    int blocked;
+    const float* logmel;
+    long long n_frames;
+    int frames_per_clip, t_out;
 };
 int launch_gcc_gemm(const GccGemmArgs& g, int num_sms, cudaStream_t st);
 
@@ -63,7 +64,8 @@ struct ExtractArgs {
     int gather_unrolled;      // every mel segment has <= 3 pieces and n_mels <= 64: gather_pairs
     int gcc_tc;               // MIC: write fp16 pair phasors to gcc_rows; the tensor-core GEMM does the lag projection
     int t_g;                  // frames per clip that have a stored row (min(t_raw, t_out))
-    float* gcc_rows;          // [n_clips * t_g * 6][512] words (fp16 re/im), A operand of gcc_gemm
+    float* gcc_rows;          // tile-blocked fp16 pair phasors, A operand of gcc_gemm (21 frames = 126 rows per tile)
+    float* gcc_logmel;        // [n_clips * t_g][n_mels][4] un-clamped log-mel; gcc_gemm assembles the complete rows
     int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
     int fpw;                  // frames per warp per super-chunk
     int assign_blocked;       // 0: super-chunk sc -> CTA sc mod grid; 1: each CTA walks one contiguous range
@@ -154,7 +156,12 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
                                      : gather_phase<MODE, 0>(E, tb, acc, a.n_mels, lane);
         __syncwarp();
         if constexpr (tc) {
-            if (t < a.t_g) gcc_tc_copy_out(S0, S1, a.gcc_rows, ((long long)clip * a.t_g + t) * 6, lane);
+            if (t < a.t_g) {
+                const long long frame = (long long)clip * a.t_g + t;
+                gcc_tc_copy_out(S0, S1, a.gcc_rows, (frame / 21) * 128 + (frame % 21) * 6, lane);
+                float* lm = a.gcc_logmel + frame * (a.n_mels * 4);     // log-mel only; gcc_gemm writes the feature row
+                for (int e = lane; e < a.n_mels * 4; e += 32) lm[e] = acc[(e >> 2) * C + (e & 3)];
+            }
         }
         if constexpr (MODE == MODE_MIC && !tc) {
             gcc_stage1<R, 0>(S0, S1, E, lane);
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
             gcc_stage2<R, 2>(E, tb, acc, a.n_mels, lane);
             __syncwarp();
         }
-        if (row != nullptr) store_row(acc, row_elems, row, lane);
+        if (!tc && row != nullptr) store_row(acc, row_elems, row, lane);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if (clip != run_clip) {
@@ -335,14 +342,15 @@ static int launch_mode(const seld_plan* plan, const ExtractArgs& a, cudaStream_t
     GccGemmArgs g{};
     g.A = reinterpret_cast<const __half*>(a.gcc_rows);
     g.Bt = reinterpret_cast<const __half*>(plan->gcc_bt);
-    g.rows = (long long)a.n_clips * a.t_g * 6;
+    g.n_frames = (long long)a.n_clips * a.t_g;
+    g.n_tiles = (g.n_frames + 20) / 21;
     g.scale = 1.0f / 512.0f;
     g.dense_out = nullptr;
+    g.dense_rows = 0;
     g.feat = a.out;
+    g.logmel = a.gcc_logmel;
     g.frames_per_clip = a.t_g;
     g.t_out = a.t_out;
-    g.n_ch = 10;
-    g.blocked = 1;
     return launch_gcc_gemm(g, plan->num_sms, stream);
 }
 
@@ -478,16 +486,23 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
     }
     if (e == cudaSuccess && mode == SELD_MODE_MIC && n_fft == 1024 && n_mels == 64) {
         // B^T of the tensor-core lag projection: [64 lags][1024] fp16, x512 (see gcc_gemm.cu / seld_b200.tables.gcc_basis)
+        // stored as the operand image gcc_gemm.cu bulk-copies: [16 chunks][64 rows][128 bytes, 16-byte units XOR (row % 8)]
         std::vector<__half> bt((size_t)64 * 1024);
         const double two_pi = 2.0 * 3.14159265358979323846264338327950288;
         for (int j = 0; j < 64; ++j) {
             const int lag = j - 32;
-            bt[(size_t)j * 1024 + 0] = __float2half(float(512.0 / 1024.0));
-            bt[(size_t)j * 1024 + 1] = __float2half(float(((lag & 1) ? -512.0 : 512.0) / 1024.0));
-            for (int k = 1; k < 512; ++k) {
-                const double ang = two_pi * double(k) * double(lag) / 1024.0;
-                bt[(size_t)j * 1024 + 2 * k] = __float2half(float(cos(ang)));              // 512 * 2 cos / 1024
-                bt[(size_t)j * 1024 + 2 * k + 1] = __float2half(float(-sin(ang)));
+            for (int K = 0; K < 1024; ++K) {
+                double val;
+                const int k = K >> 1;
+                if (K == 0) val = 0.5;                                     // 512 * (1/1024): DC
+                else if (K == 1) val = (lag & 1) ? -0.5 : 0.5;             // Nyquist: cos(pi lag) / 1024 * 512
+                else {
+                    const double ang = two_pi * double(k) * double(lag) / 1024.0;
+                    val = (K & 1) ? -sin(ang) : cos(ang);                  // 512 * (2/1024) * {cos, -sin}
+                }
+                const int c = K >> 6, kk = K & 63;
+                const size_t idx = (size_t)c * 4096 + (size_t)j * 64 + (size_t)(((kk >> 3) ^ (j & 7)) << 3) + (kk & 7);
+                bt[idx] = __float2half(float(val));
             }
         }
         up((void**)&plan->gcc_bt, bt.data(), sizeof(__half) * bt.size());
@@ -537,8 +552,9 @@ static int64_t workspace_bytes_for(const seld_plan* plan, int n_clips, int64_t n
     if (!plan || plan->gcc_bt == nullptr || n_clips <= 0 || n_samples <= 0 || t_out <= 0) return 0;
     const int64_t t_raw = 1 + n_samples / plan->hop;
     const int64_t t_g = t_raw < t_out ? t_raw : t_out;
-    const int64_t rows = (int64_t)n_clips * t_g * 6;    // one 2 KB fp16 row per (frame, pair), in whole 128-row tiles
-    return ((rows + 127) / 128) * 128 * 2048;
+    const int64_t frames = (int64_t)n_clips * t_g;
+    const int64_t tiles = (frames + 20) / 21;            // 21 frames (126 rows of 2 KB fp16 phasors) per 128-row tile
+    return tiles * 128 * 2048 + frames * 64 * 4 * 4;     // + the log-mel side buffer
 }
 
 static int extract_common(seld_plan_t plan, const void* wav_void, int layout, int n_clips, int64_t n_samples, int t_out,
@@ -579,6 +595,10 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
         a.gcc_tc = (need > 0 && workspace_dev != nullptr && workspace_bytes >= need &&
                     reinterpret_cast<uintptr_t>(workspace_dev) % 16 == 0) ? 1 : 0;
         a.gcc_rows = static_cast<float*>(workspace_dev);
+        {
+            const int64_t frames = (int64_t)n_clips * a.t_g;
+            a.gcc_logmel = a.gcc_rows + ((frames + 20) / 21) * 128 * 512;
+        }
     }
     a.gather_unrolled = plan->max_pieces_per_seg <= 3 && plan->n_mels <= 64;
     // frames [t_lo, t_hi) need no reflection: t*hop - n_fft/2 >= 0 and t*hop + n_fft/2 <= n_samples

@@ -624,16 +624,21 @@ inline void gather_pairs_publish(const float2* P, const Tables& tb, int n_mels, 
 // rows: [6][512] 32-bit words (one fp16 (re, im) pair per bin; word 0 = (Re P[0], Re P[N/2])).  Lane l copies bins
 // l, l+32, ...: coalesced 128-byte stores.  N = 1024 only.
 #if defined(__CUDACC__)
-// Destination layout = what gcc_gemm.cu reads with fully contiguous 16 KB copies: [tile][chunk][128 rows][32 words],
-// row = first_row + pair, tile = row / 128, chunk = bin / 32.
-__device__ __forceinline__ void gcc_tc_copy_out(const float2* S0, const float2* S1, float* scratch, long long first_row,
+// Destination = the UMMA operand image gcc_gemm.cu bulk-copies straight into shared memory (K-major SWIZZLE_128B):
+// per (tile, chunk of 32 bins) one 16 KB block; row r of the chunk is 128 contiguous bytes at r * 128 and its 16-byte
+// unit u sits at unit position u ^ (r % 8).  Lane l holds bin k = l + 32 * chunk = word l of the row, so every store
+// instruction writes one full 128-byte line.  tile_row = tile * 128 + row-in-tile of the frame's first pair.
+__device__ __forceinline__ void gcc_tc_copy_out(const float2* S0, const float2* S1, float* scratch, long long tile_row,
                                                 int lane) {
     constexpr int N = 1024;
+    const long long tile = tile_row >> 7;
+    const int r_first = int(tile_row & 127);
+    float* tbase = scratch + tile * (16 * 4096);
 #pragma unroll
     for (int pp = 0; pp < 3; ++pp) {                 // slot pp holds pairs 2pp (.x) and 2pp + 1 (.y)
-        const long long ra = first_row + 2 * pp, rb = ra + 1;
-        float* dst0 = scratch + ((ra >> 7) * 16 * 128 + (ra & 127)) * 32 + lane;
-        float* dst1 = scratch + ((rb >> 7) * 16 * 128 + (rb & 127)) * 32 + lane;
+        const int ra = r_first + 2 * pp, rb = ra + 1;
+        float* dst0 = tbase + ra * 32 + ((((lane >> 2) ^ (ra & 7)) << 2) | (lane & 3));
+        float* dst1 = tbase + rb * 32 + ((((lane >> 2) ^ (rb & 7)) << 2) | (lane & 3));
 #pragma unroll
         for (int i = 0; i < 16; ++i) {               // i = chunk; this lane's bin k = lane + 32 i
             const int k = lane + 32 * i;
@@ -647,8 +652,8 @@ __device__ __forceinline__ void gcc_tc_copy_out(const float2* S0, const float2* 
             } else {
                 w = (pp == 0) ? S0[k] : (pp == 1 ? S0[N - k] : S1[k]);
             }
-            dst0[i * 128 * 32] = w.x;
-            dst1[i * 128 * 32] = w.y;
+            dst0[i * 4096] = w.x;
+            dst1[i * 4096] = w.y;
         }
     }
 }

@@ -61,3 +61,25 @@ def gcc_basis(n_fft: int = 1024, n_lags: int = 64) -> np.ndarray:
     bt[:, 2::2] = 2.0 * np.cos(ang) / n_fft
     bt[:, 3::2] = -2.0 * np.sin(ang) / n_fft
     return (bt * GCC_BASIS_SCALE).astype(np.float16)
+
+
+def gcc_operand_image(mat: np.ndarray) -> np.ndarray:
+    """Row-major float16 [rows, 1024] -> the UMMA operand image seld_gcc_gemm consumes (K-major SWIZZLE_128B): rows are
+    padded to a multiple of 128 for the A operand (rows == 64: the B^T operand, one 64-row block per chunk); per block
+    of rows, 16 chunks of 64 K-elements; inside a chunk row r is 128 contiguous bytes whose 16-byte unit u is stored at
+    unit position u ^ (r % 8).  (The fused extractor writes this layout directly.)"""
+    mat = np.ascontiguousarray(mat, dtype=np.float16)
+    rows, k = mat.shape
+    assert k == 1024
+    block = 64 if rows == 64 else 128
+    pad = (-rows) % block
+    if pad:
+        mat = np.concatenate([mat, np.zeros((pad, 1024), np.float16)], 0)
+    n_blocks = mat.shape[0] // block
+    x = mat.reshape(n_blocks, block, 16, 8, 8)                  # [block][row][chunk][unit][e]
+    out = np.empty_like(x)
+    r = np.arange(block)
+    for u in range(8):
+        out[:, r, :, u ^ (r % 8), :] = x[:, r, :, u, :]
+    out = out.transpose(0, 2, 1, 3, 4)                          # [block][chunk][row][unit][e]
+    return np.ascontiguousarray(out if rows != 64 else out[0])

@@ -7,15 +7,18 @@ pytestmark = pytest.mark.gpu
 
 
 def _run(a16, bt16, scale):
-    from seld_b200 import _lib
+    """a16 [rows, 1024], bt16 [64, 1024] float16 CUDA tensors (row-major) -> packs the operand images, runs the kernel."""
+    from seld_b200 import _lib, tables
+    a_img = torch.from_numpy(tables.gcc_operand_image(a16.cpu().numpy())).cuda()
+    bt_img = torch.from_numpy(tables.gcc_operand_image(bt16.cpu().numpy())).cuda()
     out = torch.empty(a16.shape[0], 64, dtype=torch.float32, device='cuda')
-    _lib.check(_lib.load().seld_gcc_gemm(_lib.ptr(a16), _lib.ptr(bt16), a16.shape[0], float(scale), _lib.ptr(out),
+    _lib.check(_lib.load().seld_gcc_gemm(_lib.ptr(a_img), _lib.ptr(bt_img), a16.shape[0], float(scale), _lib.ptr(out),
                                          _lib.current_stream_ptr()))
     torch.cuda.synchronize()
     return out
 
 
-@pytest.mark.parametrize('rows', [128, 37, 1000, 128 * 148 * 3 + 5])
+@pytest.mark.parametrize('rows', [128, 37, 1000, 128 * 148 * 5 + 5])
 def test_gemm_matches_float32_matmul(rows):
     g = torch.Generator().manual_seed(rows)
     a = (torch.rand(rows, 1024, generator=g) * 2 - 1).to(torch.float16).cuda()
