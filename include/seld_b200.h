@@ -109,6 +109,19 @@ SELD_API int seld_extract_pcm16(seld_plan_t plan, const int16_t* pcm_dev, int n_
                                 float* feat_raw_dev, uint32_t* clip_max_key_dev, void* workspace_dev, int64_t workspace_bytes,
                                 void* stream);
 
+/*
+ * On-the-fly form for training batches (BASELINE.json config 5): every "clip" is a chunk cut from a
+ * longer recording WITH its real context, chunk[c] = samples [s0 - n_fft/2, s0 + (t - 1) * hop + n_fft/2), and frame t
+ * starts at chunk sample t * hop (no centring, no reflection), so the rows equal rows s0/hop .. of the full-clip
+ * extraction bit for bit.  n_samples >= n_fft; frames = 1 + (n_samples - n_fft) / hop.  chunk_max_key_dev receives the
+ * chunk maxima; for the reference's clip-global top_db pass the cached clip maxima to seld_finalize instead.
+ * (With a MIC workspace, size it with the chunk's frame count: n_chunks * frames * 6 rows of 2 KB, rounded up to
+ * 21-frame tiles, plus frames * 1 KB.)
+ */
+SELD_API int seld_extract_chunks(seld_plan_t plan, const float* wav_dev, int layout, int n_chunks, int64_t n_samples, int t_out,
+                                 float* feat_raw_dev, uint32_t* chunk_max_key_dev, void* workspace_dev, int64_t workspace_bytes,
+                                 void* stream);
+
 SELD_API int seld_clip_max_decode(const uint32_t* clip_max_key_dev, int n_clips, float* clip_max_dev, void* stream);
 
 /*

@@ -27,6 +27,7 @@ SIGNATURES = {
     'seld_plan_out_channels': (_i, [_vp]),
     'seld_plan_num_frames': (_i64, [_vp, _i64]),
     'seld_extract': (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _i64, _vp]),
+    'seld_extract_chunks': (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _i64, _vp]),
     'seld_extract_workspace_bytes': (_i64, [_vp, _i, _i64, _i]),
     'seld_extract_pcm16': (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i64, _vp]),
     'seld_clip_max_decode': (_i, [_vp, _i, _vp, _vp]),

@@ -67,6 +67,7 @@ struct ExtractArgs {
     float* gcc_rows;          // tile-blocked fp16 pair phasors, A operand of gcc_gemm (21 frames = 126 rows per tile)
     float* gcc_logmel;        // [n_clips * t_g][n_mels][4] un-clamped log-mel; gcc_gemm assembles the complete rows
     int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
+    int origin;               // frame t starts at sample t*hop - n_fft/2 + origin (0: centred STFT; n_fft/2: uncentred chunks)
     int fpw;                  // frames per warp per super-chunk
     int assign_blocked;       // 0: super-chunk sc -> CTA sc mod grid; 1: each CTA walks one contiguous range
     int fsc;                  // frames per super-chunk (<= warps * fpw); odd => CTA start phases cover all 128 B offsets
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
                 src.n_samples = a.n_samples;
                 if (a.layout == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
                 else { src.chan_stride = 1; src.samp_stride = 4; }
-                const long long start = (long long)t * a.hop - G::N / 2;
+                const long long start = (long long)t * a.hop - G::N / 2 + a.origin;
 #pragma unroll 1
                 for (int pr = 0; pr < 2; ++pr) {
                     float2 v[R];
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
             src.n_samples = a.n_samples;
             if constexpr (LAYOUT == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
             else { src.chan_stride = 1; src.samp_stride = 4; }
-            start = (long long)t * a.hop - G::N / 2;
+            start = (long long)t * a.hop - G::N / 2 + a.origin;
         };
         long long g = frame_index(sc, fi);
         float2 raw[R];
@@ -548,9 +549,10 @@ int64_t seld_plan_num_frames(seld_plan_t plan, int64_t n_samples) {
     return 1 + n_samples / plan->hop;
 }
 
-static int64_t workspace_bytes_for(const seld_plan* plan, int n_clips, int64_t n_samples, int t_out) {
+static int64_t workspace_bytes_for(const seld_plan* plan, int n_clips, int64_t n_samples, int t_out, bool centered = true) {
     if (!plan || plan->gcc_bt == nullptr || n_clips <= 0 || n_samples <= 0 || t_out <= 0) return 0;
-    const int64_t t_raw = 1 + n_samples / plan->hop;
+    if (!centered && n_samples < plan->n_fft) return 0;
+    const int64_t t_raw = centered ? 1 + n_samples / plan->hop : 1 + (n_samples - plan->n_fft) / plan->hop;
     const int64_t t_g = t_raw < t_out ? t_raw : t_out;
     const int64_t frames = (int64_t)n_clips * t_g;
     const int64_t tiles = (frames + 20) / 21;            // 21 frames (126 rows of 2 KB fp16 phasors) per 128-row tile
@@ -559,16 +561,17 @@ static int64_t workspace_bytes_for(const seld_plan* plan, int n_clips, int64_t n
 
 static int extract_common(seld_plan_t plan, const void* wav_void, int layout, int n_clips, int64_t n_samples, int t_out,
                           float* feat_raw_dev, uint32_t* clip_max_key_dev, void* workspace_dev, int64_t workspace_bytes,
-                          void* stream) {
+                          void* stream, bool centered = true) {
     const float* wav_dev = static_cast<const float*>(wav_void);
     if (!plan || !wav_dev || !feat_raw_dev || !clip_max_key_dev) { set_error("null argument"); return SELD_EINVAL; }
     if (layout != LAYOUT_PLANAR_CL && layout != LAYOUT_INTERLEAVED_LC && layout != LAYOUT_PCM16_LC) { set_error("invalid layout"); return SELD_EINVAL; }
     if (reinterpret_cast<uintptr_t>(wav_void) % 16 != 0) { set_error("wav_dev must be 16-byte aligned"); return SELD_EINVAL; }
     if (n_clips < 0 || t_out < 0) { set_error("negative size"); return SELD_EINVAL; }
-    if (n_samples <= plan->n_fft / 2) {
+    if (centered && n_samples <= plan->n_fft / 2) {
         set_error("reflect padding needs n_fft/2 < number of samples (torch.stft raises here too)");
         return SELD_EINVAL;
     }
+    if (!centered && n_samples < plan->n_fft) { set_error("an uncentred chunk needs at least n_fft samples"); return SELD_EINVAL; }
     if (n_clips == 0) return SELD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ExtractArgs a;
@@ -576,7 +579,8 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
     a.layout = layout;
     a.n_clips = n_clips;
     a.n_samples = n_samples;
-    a.t_raw = int(1 + n_samples / plan->hop);
+    a.t_raw = centered ? int(1 + n_samples / plan->hop) : int(1 + (n_samples - plan->n_fft) / plan->hop);
+    a.origin = centered ? 0 : plan->n_fft / 2;
     a.t_out = t_out;
     a.t_tot = a.t_raw > t_out ? a.t_raw : t_out;
     a.out = feat_raw_dev;
@@ -591,7 +595,7 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
     a.e_bytes = plan->e_bytes;
     a.t_g = a.t_raw < t_out ? a.t_raw : t_out;
     {
-        const int64_t need = workspace_bytes_for(plan, n_clips, n_samples, t_out);
+        const int64_t need = workspace_bytes_for(plan, n_clips, n_samples, t_out, centered);
         a.gcc_tc = (need > 0 && workspace_dev != nullptr && workspace_bytes >= need &&
                     reinterpret_cast<uintptr_t>(workspace_dev) % 16 == 0) ? 1 : 0;
         a.gcc_rows = static_cast<float*>(workspace_dev);
@@ -604,8 +608,8 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
     // frames [t_lo, t_hi) need no reflection: t*hop - n_fft/2 >= 0 and t*hop + n_fft/2 <= n_samples
     {
         const long long half = plan->n_fft / 2;
-        long long lo = (half + plan->hop - 1) / plan->hop;
-        long long hi = (n_samples >= half) ? (n_samples - half) / plan->hop + 1 : 0;
+        long long lo = centered ? (half + plan->hop - 1) / plan->hop : 0;
+        long long hi = centered ? ((n_samples >= half) ? (n_samples - half) / plan->hop + 1 : 0) : a.t_raw;
         if (hi > a.t_raw) hi = a.t_raw;
         if (lo > hi) lo = hi;
         a.t_lo = int(lo);
@@ -638,6 +642,14 @@ int seld_extract_pcm16(seld_plan_t plan, const int16_t* pcm_dev, int n_clips, in
                        void* stream) {
     return extract_common(plan, pcm_dev, LAYOUT_PCM16_LC, n_clips, n_samples, t_out, feat_raw_dev, clip_max_key_dev,
                           workspace_dev, workspace_bytes, stream);
+}
+
+int seld_extract_chunks(seld_plan_t plan, const float* wav_dev, int layout, int n_chunks, int64_t n_samples, int t_out,
+                        float* feat_raw_dev, uint32_t* chunk_max_key_dev, void* workspace_dev, int64_t workspace_bytes,
+                        void* stream) {
+    if (layout != SELD_LAYOUT_PLANAR_CL && layout != SELD_LAYOUT_INTERLEAVED_LC) { set_error("invalid layout"); return SELD_EINVAL; }
+    return extract_common(plan, wav_dev, layout, n_chunks, n_samples, t_out, feat_raw_dev, chunk_max_key_dev, workspace_dev,
+                          workspace_bytes, stream, /*centered=*/false);
 }
 
 int seld_clip_max_decode(const uint32_t* clip_max_key_dev, int n_clips, float* clip_max_dev, void* stream) {

@@ -38,7 +38,7 @@ def _workspace(device, n_bytes):
 
 
 def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', out=None, key=None,
-                  use_tensor_cores=True, **kwargs):
+                  use_tensor_cores=True, center=True, **kwargs):
     """wav: CUDA float32 [n_clips, 4, L] (layout='planar') or [n_clips, L, 4] ('interleaved'), or CUDA int16
     [n_clips, L, 4] (16-bit PCM in WAV frame order, decoded as sample / 32768 like torchaudio.load).
 
@@ -74,7 +74,12 @@ def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='p
         n_samples += 2 * pad
     with torch.cuda.device(wav.device):
         plan = get_plan(sample_rate, mode=mode, n_mels=n_mels, **kwargs)
-        t_raw = plan.num_frames(n_samples)
+        if center:
+            t_raw = plan.num_frames(n_samples)
+        else:                                     # chunks carrying their own context: frame t starts at sample t * hop
+            if pcm16 or n_samples < plan.n_fft:
+                raise ValueError('center=False needs float32 chunks of at least n_fft samples')
+            t_raw = 1 + (n_samples - plan.n_fft) // plan.hop_length
         if t_out is None:
             t_out = t_raw
         shape = (n_clips, int(t_out), plan.n_mels, plan.n_out_ch)
@@ -88,17 +93,43 @@ def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='p
             key = torch.empty(n_clips, dtype=torch.int32, device=wav.device)
         lib = _lib.load()
         ws, ws_bytes = None, 0
-        if use_tensor_cores:
+        if use_tensor_cores and center:
             ws_bytes = int(lib.seld_extract_workspace_bytes(plan.handle, n_clips, n_samples, int(t_out)))
             if ws_bytes > 0:
                 ws = _workspace(wav.device, ws_bytes)
         if pcm16:
             _lib.check(lib.seld_extract_pcm16(plan.handle, _lib.ptr(wav), n_clips, n_samples, int(t_out),
                                               _lib.ptr(out), _lib.ptr(key), _lib.ptr(ws), ws_bytes, _lib.current_stream_ptr()))
+        elif not center:
+            _lib.check(lib.seld_extract_chunks(plan.handle, _lib.ptr(wav), code, n_clips, n_samples, int(t_out),
+                                               _lib.ptr(out), _lib.ptr(key), None, 0, _lib.current_stream_ptr()))
         else:
             _lib.check(lib.seld_extract(plan.handle, _lib.ptr(wav), code, n_clips, n_samples, int(t_out),
                                         _lib.ptr(out), _lib.ptr(key), _lib.ptr(ws), ws_bytes, _lib.current_stream_ptr()))
     return out, key
+
+
+def clip_max_keys(max_db):
+    """float32 per-clip maxima (dB) -> the order-preserving int32 keys finalize_ / partial_statistics expect (cached
+    clip maxima of an earlier full-clip pass)."""
+    bits = max_db.to(torch.float32).contiguous().view(torch.int32)
+    return torch.where(bits < 0, ~bits, bits | torch.tensor(-2 ** 31, dtype=torch.int32, device=bits.device))
+
+
+def training_batch(wav_chunks, sample_rate, clip_max_db, mean, std, mode='foa', n_mels=64, layout='planar',
+                   time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=0, sample_offset=0, **kwargs):
+    """BASELINE.json config 5(ii): wav chunks with context -> normalised, masked training batch [B, T, n_mels, C].
+
+    wav_chunks: CUDA float32 [B, 4, (T - 1) * hop + n_fft] -- chunk b holds the samples from n_fft/2 before its first
+    frame centre to n_fft/2 after its last; clip_max_db: [B] cached maxima of the clips the chunks were cut from
+    (so the top_db floor is the reference's clip-global one); mean/std: the dataset statistics.  Three launches:
+    fused extract -> clamp + normalise -> fused time/frequency masking (reference train.py:157-160)."""
+    from . import transforms
+    feat, _ = extract_batch(wav_chunks, sample_rate, mode=mode, n_mels=n_mels, layout=layout, center=False, **kwargs)
+    finalize_(feat, clip_max_keys(clip_max_db.to(feat.device)), None, mean, std)
+    if time_mask or freq_mask:
+        transforms.mask_batch_(feat, time_mask, freq_mask, period=period, seed=seed, sample_offset=sample_offset)
+    return feat
 
 
 def clip_max_db(clip_max_key):

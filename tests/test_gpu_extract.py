@@ -125,3 +125,28 @@ def test_mic_tensor_core_gcc_matches_cuda_core_path():
         assert torch.equal(ka, kb) and torch.equal(a[..., :4], b[..., :4])          # log-mel part is the same code
         err = float((a[..., 4:] - b[..., 4:]).abs().max())
         assert err <= 3e-4, err
+
+
+def test_on_the_fly_chunks_equal_full_clip_rows():
+    """Config 5(ii): chunks cut with +-n_fft/2 of real context reproduce the corresponding rows of the full-clip
+    features bit for bit (same samples, same code path), and the fused training batch == slice -> normalise -> mask."""
+    from seld_b200 import pipeline, transforms
+    from seld_b200.synth import make_clips
+    n_clips, L, T = 3, 480 * 700, 300
+    wav = make_clips(range(500, 500 + n_clips), L).cuda()
+    full, key = pipeline.extract_batch(wav, 24000, mode='foa', **PROD)
+    cmax = pipeline.clip_max_db(key)
+    starts = [(0, 100), (1, 7), (2, 399), (1, 250)]                          # (clip, first frame); frames t0 .. t0 + 299
+    chunks = torch.stack([wav[c, :, t0 * 480 - 512: (t0 + T - 1) * 480 + 512] for c, t0 in starts]).contiguous()
+    assert chunks.shape == (4, 4, (T - 1) * 480 + 1024)
+    raw, _ = pipeline.extract_batch(chunks, 24000, mode='foa', center=False, **PROD)
+    for i, (c, t0) in enumerate(starts):
+        assert torch.equal(raw[i], full[c, t0:t0 + T])
+    mean = full.mean(dim=(0, 1), keepdim=True)
+    std = full.std(dim=(0, 1), keepdim=True)
+    batch = pipeline.training_batch(chunks, 24000, cmax[[c for c, _ in starts]], mean, std, seed=11, sample_offset=40, **PROD)
+    want = torch.stack([full[c, t0:t0 + T] for c, t0 in starts]).clone()
+    pipeline.finalize_(want, key[[c for c, _ in starts]].contiguous(), None, mean, std)
+    transforms.mask_batch_(want, (24, 1), (16, 1), seed=11, sample_offset=40)
+    assert torch.equal(batch, want)
+    assert pipeline.clip_max_keys(cmax).equal(key)
