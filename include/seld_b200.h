@@ -175,6 +175,16 @@ SELD_API int seld_mask(void* x_dev, int dtype, int64_t n_samples, int64_t t, int
               const int64_t* op_seed2_dev, int32_t* draws_out_dev, void* stream);
 
 /*
+ * Per-sample channel gather + sign flip, in place: the data movement of the reference's batch-level spatial
+ * augmentations (foa_intensity_vec_aug transforms.py:78-114, acs_aug :155-199).  x_dev is viewed as float32
+ * [n_samples][outer][n_chan][inner]:  x[b, o, c, j] <- sign[b, c] * x[b, o, perm[b, c], j].
+ * Features [B, T, F, C]: outer = T*F, inner = 1.  Label coordinates [B, T, 4, n_classes]: outer = T, n_chan = 4,
+ * inner = n_classes.  perm_dev int32 [n_samples][n_chan], sign_dev float32 [n_samples][n_chan]; n_chan <= 20.
+ */
+SELD_API int seld_channel_remap(float* x_dev, int64_t n_samples, int64_t outer, int n_chan, int64_t inner, const int32_t* perm_dev,
+                                const float* sign_dev, void* stream);
+
+/*
  * Stand-alone stages (API parity with the reference's public helpers; the hot path is seld_extract).
  *   seld_complex_spec     reference feature_extractor.py:153-173; spec_dev [n_chan][T][F] complex64 (frame-major;
  *                         the Python wrapper returns the [C, F, T] transposed view)

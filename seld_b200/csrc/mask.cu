@@ -194,3 +194,53 @@ extern "C" int seld_mask(void* x_dev, int dtype, int64_t n_samples, int64_t t, i
         default: set_error("unsupported dtype"); return SELD_EUNSUPPORTED;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Per-sample channel gather + sign flip, in place: the data movement of the reference's batch-level spatial
+// augmentations (foa_intensity_vec_aug transforms.py:78-114, acs_aug :155-199), which only permute / negate channels of
+// the features [B, T, F, C] and of the label coordinates [B, T, 4, n_classes].  x is viewed as [n][outer][C][inner]:
+//     x[b, o, c, j] <- sign[b, c] * x[b, o, perm[b, c], j]
+namespace seld {
+template <int MAXC>
+__global__ void __launch_bounds__(256) channel_remap_kernel(float* __restrict__ x, long long n_samples, long long outer, int C,
+                                                            long long inner, const int* __restrict__ perm,
+                                                            const float* __restrict__ sign) {
+    const long long per_sample = outer * inner;
+    const long long total = n_samples * per_sample;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long b = i / per_sample, r = i - b * per_sample;
+        const long long o = r / inner, j = r - o * inner;
+        float* p = x + ((b * outer + o) * C) * inner + j;
+        float v[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) v[c] = (c < C) ? p[(long long)c * inner] : 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            if (c < C) {
+                const int src = perm[b * C + c];
+                float val = 0.f;
+#pragma unroll
+                for (int s = 0; s < MAXC; ++s) val = (s == src) ? v[s] : val;          // register select, no local memory
+                p[(long long)c * inner] = sign[b * C + c] * val;
+            }
+        }
+    }
+}
+}  // namespace seld
+
+extern "C" int seld_channel_remap(float* x_dev, int64_t n_samples, int64_t outer, int n_chan, int64_t inner, const int32_t* perm_dev,
+                                  const float* sign_dev, void* stream) {
+    if (!x_dev || !perm_dev || !sign_dev || n_samples < 0 || outer < 0 || inner < 1 || n_chan < 1) { set_error("bad argument"); return SELD_EINVAL; }
+    if (n_chan > 20) { set_error("at most 20 channels"); return SELD_EUNSUPPORTED; }
+    const long long total = n_samples * outer * inner;
+    if (total == 0) return SELD_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_chan <= 4) channel_remap_kernel<4><<<(int)blocks, 256, 0, st>>>(x_dev, n_samples, outer, n_chan, inner, perm_dev, sign_dev);
+    else if (n_chan <= 10) channel_remap_kernel<10><<<(int)blocks, 256, 0, st>>>(x_dev, n_samples, outer, n_chan, inner, perm_dev, sign_dev);
+    else channel_remap_kernel<20><<<(int)blocks, 256, 0, st>>>(x_dev, n_samples, outer, n_chan, inner, perm_dev, sign_dev);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}

@@ -21,7 +21,8 @@ import torch
 
 from . import _lib
 
-__all__ = ['mask', 'simple_mask', 'mask_batch_', 'set_seed', 'set_counter_seed']
+__all__ = ['mask', 'simple_mask', 'mask_batch_', 'set_seed', 'set_counter_seed', 'foa_intensity_vec_aug', 'acs_aug',
+           'mic_gcc_perm', 'channel_list', 'split_total_labels_to_sed_doa']
 
 _MAXINT32 = 2 ** 31 - 1
 _state = threading.local()
@@ -170,3 +171,134 @@ def mask_batch_(x, time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, 
         sample_offset = 0
     return _launch(x, b, t, 1, f, c, int(period), tm, int(tn), fm, int(fn), int(seed) & (2 ** 64 - 1), int(sample_offset),
                    _lib.RNG_PHILOX_COUNTER, None, return_draws)
+
+
+# --------------------------------------------------------------------------- batch-level spatial augmentations (f1)
+STREAM_IV_AUG, STREAM_ACS_AUG = 0x100, 0x101        # Philox stream ids (masking uses the chunk index < 2**24 there)
+
+# reference transforms.py:143-152 (arXiv:2101.02919, table 1): [[mic channel], [foa channel]] for the 8 swaps
+channel_list = [
+    [[1, 3, 0, 2], [0, -3, -2, 1]],
+    [[3, 1, 2, 0], [0, -3, 2, -1]],
+    [[0, 1, 2, 3], [0, 1, 2, 3]],
+    [[1, 0, 3, 2], [0, -1, -2, 3]],
+    [[2, 0, 3, 1], [0, 3, -2, -1]],
+    [[0, 2, 1, 3], [0, 3, 2, 1]],
+    [[3, 2, 1, 0], [0, -1, 2, -3]],
+    [[2, 3, 0, 1], [0, 1, -2, -3]],
+]
+_GCC_PAIRS = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+
+
+def split_total_labels_to_sed_doa(x, y):
+    """reference transforms.py:117-119."""
+    n_classes = y.shape[-1] // 4
+    return x, (y[..., :n_classes], y[..., n_classes:])
+
+
+def mic_gcc_perm(mic_perm):
+    """reference transforms.py:122-139: microphone permutation [B, 4] -> permutation of the 6 GCC pair channels
+    (pair order (0,1),(0,2),(0,3),(1,2),(1,3),(2,3)); exact table pinned by transforms_test.py:64-73."""
+    mp = np.asarray(mic_perm.cpu() if isinstance(mic_perm, torch.Tensor) else mic_perm, dtype=np.int64)
+    decode = np.array([[0, 0, 1, 2], [0, 0, 3, 4], [1, 3, 0, 5], [2, 4, 5, 0]], dtype=np.int64)
+    out = np.empty((mp.shape[0], 6), dtype=np.int32)
+    for j, (a, b) in enumerate(_GCC_PAIRS):
+        out[:, j] = decode[mp[:, a], mp[:, b]]
+    return torch.from_numpy(out) if isinstance(mic_perm, torch.Tensor) else out
+
+
+def _remap_(t, outer, n_chan, inner, perm, sign):
+    """x[b, o, c, j] <- sign[b, c] * x[b, o, perm[b, c], j] in place on a contiguous float32 CUDA tensor."""
+    perm_d = torch.as_tensor(np.ascontiguousarray(perm, dtype=np.int32), device=t.device)
+    sign_d = torch.as_tensor(np.ascontiguousarray(sign, dtype=np.float32), device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().seld_channel_remap(_lib.ptr(t), t.shape[0], outer, n_chan, inner, _lib.ptr(perm_d),
+                                                  _lib.ptr(sign_d), _lib.current_stream_ptr()))
+
+
+def _aug_inputs(x, y):
+    _lib.require_device()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    xs = torch.as_tensor(x).to(device=dev, dtype=torch.float32).contiguous()
+    ys = torch.as_tensor(y).to(device=dev, dtype=torch.float32).contiguous()
+    if xs.data_ptr() == (x.data_ptr() if isinstance(x, torch.Tensor) else 0):
+        xs = xs.clone()                                  # the reference returns new tensors (tf.identity)
+    if ys.data_ptr() == (y.data_ptr() if isinstance(y, torch.Tensor) else 0):
+        ys = ys.clone()
+    return xs, ys
+
+
+def _draw_seed(n, seed, sample_offset):
+    if seed is None:
+        seed, first = _take_samples(n)
+        return seed, first if sample_offset is None else sample_offset
+    return int(seed) & (2 ** 64 - 1), 0 if sample_offset is None else int(sample_offset)
+
+
+def foa_intensity_vec_aug(x, y, seed=None, sample_offset=None, return_draws=False):
+    """reference transforms.py:78-114 for x [B, T, F, 7], y [B, T, 4*n_classes]: per sample, random sign flips of the
+    three intensity / coordinate axes and a random x<->y... swap ([0,1,2] or the reference's [2,1,0] channel order),
+    applied consistently to the FOA channels 1..3, the intensity vectors 4..6 and the label coordinates.
+    Draws: Philox word 0..2 & 1 = flips, word 3 & 1 = swap, per global sample index."""
+    from . import philox
+    xs, ys = _aug_inputs(x, y)
+    b = xs.shape[0]
+    if xs.shape[-1] != 7 or ys.shape[-1] % 4:
+        raise ValueError('x must be [B, T, F, 7] and y [B, T, 4*n_classes]')
+    seed, first = _draw_seed(b, seed, sample_offset)
+    w = philox.sample_words(seed, first, b, STREAM_IV_AUG)
+    flip = (w[:, :3] & 1).astype(np.int64)                              # tf.random.uniform([B, 3], 0, 2)
+    swap = (w[:, 3] & 1).astype(np.int64)                               # tf.random.uniform([B, 1], maxval=2)
+    perm = np.stack([2 * swap, np.ones_like(swap), 2 - 2 * swap], 1)    # [p, 1, 2-p], p in {0, 2}        (:100-101)
+    check = (perm != np.array([0, 1, 2])).sum(1, keepdims=True)
+    feat_perm = (perm + check) % 3                                       # (:103-104)
+    sgn = 1 - 2 * flip                                                   # flips happen BEFORE the gather (:96-97)
+    x_perm = np.tile(np.arange(7), (b, 1))
+    x_sign = np.ones((b, 7))
+    x_perm[:, 1:4] = 1 + perm                                            # FOA channels follow `perm`     (:109)
+    x_perm[:, 4:7] = 4 + feat_perm                                       # IV channels follow `feat_perm` (:106)
+    x_sign[:, 4:7] = np.take_along_axis(sgn, feat_perm, 1)
+    y_perm = np.tile(np.arange(4), (b, 1))
+    y_sign = np.ones((b, 4))
+    y_perm[:, 1:4] = 1 + feat_perm                                       # label x, y, z                   (:107)
+    y_sign[:, 1:4] = np.take_along_axis(sgn, feat_perm, 1)
+    _remap_(xs, int(np.prod(xs.shape[1:-1])), 7, 1, x_perm, x_sign)
+    n_cls = ys.shape[-1] // 4
+    _remap_(ys, int(np.prod(ys.shape[1:-1])), 4, n_cls, y_perm, y_sign)
+    return (xs, ys, {'flip': flip, 'swap': swap}) if return_draws else (xs, ys)
+
+
+def acs_aug(x, y, seed=None, sample_offset=None, return_draws=False):
+    """reference transforms.py:155-199, audio channel swapping for x [B, T, F, 17] (4 FOA log-mel, 3 IV, 4 MIC log-mel,
+    6 GCC) and y [B, T, 4*n_classes]: one of the 8 rotations / reflections of `channel_list` per sample, applied to
+    the FOA channels, intensity vectors (with signs), microphone channels, GCC pair channels and label coordinates.
+    Draw: Philox word 0 % 8 per global sample index."""
+    from . import philox
+    xs, ys = _aug_inputs(x, y)
+    b = xs.shape[0]
+    if xs.shape[-1] != 17 or ys.shape[-1] % 4:
+        raise ValueError('x must be [B, T, F, 17] and y [B, T, 4*n_classes]')
+    seed, first = _draw_seed(b, seed, sample_offset)
+    idx = (philox.sample_words(seed, first, b, STREAM_ACS_AUG)[:, 0] % 8).astype(np.int64)
+    table = np.array(channel_list, dtype=np.int64)                      # [8, 2, 4]
+    mic_flip = table[idx, 0, :]
+    foa_flip = table[idx, 1, 1:]
+    foa_sign = np.sign(foa_flip)
+    foa_perm = foa_sign * foa_flip - 1                                   # (:176)
+    check = (foa_perm != np.array([0, 1, 2])).sum(1, keepdims=True)
+    feat_perm = (foa_perm + check) % 3                                   # (:179)
+    x_perm = np.tile(np.arange(17), (b, 1))
+    x_sign = np.ones((b, 17))
+    x_perm[:, 1:4] = 1 + foa_perm                                        # (:180)
+    x_perm[:, 4:7] = 4 + feat_perm
+    x_sign[:, 4:7] = foa_sign                                            # sign applied AFTER the gather (:182)
+    x_perm[:, 7:11] = 7 + mic_flip                                       # (:190)
+    x_perm[:, 11:17] = 11 + np.asarray(mic_gcc_perm(mic_flip))           # (:188-189)
+    y_perm = np.tile(np.arange(4), (b, 1))
+    y_sign = np.ones((b, 4))
+    y_perm[:, 1:4] = 1 + feat_perm                                       # (:183)
+    y_sign[:, 1:4] = foa_sign
+    _remap_(xs, int(np.prod(xs.shape[1:-1])), 17, 1, x_perm, x_sign)
+    n_cls = ys.shape[-1] // 4
+    _remap_(ys, int(np.prod(ys.shape[1:-1])), 4, n_cls, y_perm, y_sign)
+    return (xs, ys, {'idx': idx}) if return_draws else (xs, ys)

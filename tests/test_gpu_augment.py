@@ -1,0 +1,63 @@
+"""CUDA spatial augmentations (seld_channel_remap through transforms.foa_intensity_vec_aug / acs_aug) against the
+oracle restatement on the same draws: bit-exact (sign flips and gathers only)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import augment as A
+from seld_b200 import _lib, transforms as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('shape_x,shape_y', [((1, 10, 32, 7), (1, 2, 12)), ((5, 300, 64, 7), (5, 60, 56)), ((256, 30, 64, 7), (256, 6, 48))])
+def test_iv_aug_matches_oracle(shape_x, shape_y):
+    g = torch.Generator().manual_seed(2022)
+    x = torch.rand(shape_x, generator=g) - 0.5
+    y = torch.rand(shape_y, generator=g) - 0.5
+    nx, ny, d = T.foa_intensity_vec_aug(x.cuda(), y.cuda(), seed=99, sample_offset=1000, return_draws=True)
+    ox, oy = A.foa_intensity_vec_aug_ref(x.numpy(), y.numpy(), d['flip'], d['swap'])
+    assert np.array_equal(nx.cpu().numpy(), ox) and np.array_equal(ny.cpu().numpy(), oy)
+    # the reference's own property (transforms_test.py:46-52)
+    xf = (x.numpy()[..., -3:] != ox[..., -3:]).astype(np.float32).mean(axis=(1, 2))
+    s = shape_y[:-1] + (4, -1)
+    yf = (y.numpy().reshape(s)[..., -3:, :] != oy.reshape(s)[..., -3:, :]).astype(np.float32).mean(axis=(1, 3))
+    assert np.array_equal(xf, yf)
+    if shape_x[0] >= 256:                              # all 16 (flip, swap) combinations occur
+        assert len({(tuple(f), int(s_)) for f, s_ in zip(d['flip'], d['swap'])}) == 16
+
+
+def test_iv_aug_inputs_untouched_and_reproducible():
+    x = torch.rand(4, 20, 64, 7, device='cuda')
+    y = torch.rand(4, 4, 56, device='cuda')
+    x0, y0 = x.clone(), y.clone()
+    a = T.foa_intensity_vec_aug(x, y, seed=5)
+    b = T.foa_intensity_vec_aug(x, y, seed=5)
+    c = T.foa_intensity_vec_aug(x, y, seed=5, sample_offset=4)
+    assert torch.equal(x, x0) and torch.equal(y, y0)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert not torch.equal(a[0], c[0])
+
+
+@pytest.mark.parametrize('shape_x,shape_y', [((2, 10, 32, 17), (2, 2, 12)), ((64, 100, 64, 17), (64, 20, 56))])
+def test_acs_aug_matches_oracle(shape_x, shape_y):
+    g = torch.Generator().manual_seed(2022)
+    x = torch.rand(shape_x, generator=g) - 0.5
+    y = torch.rand(shape_y, generator=g) - 0.5
+    nx, ny, d = T.acs_aug(x.cuda(), y.cuda(), seed=3, return_draws=True)
+    ox, oy = A.acs_aug_ref(x.numpy(), y.numpy(), d['idx'])
+    assert np.array_equal(nx.cpu().numpy(), ox) and np.array_equal(ny.cpu().numpy(), oy)
+    if shape_x[0] >= 64:
+        assert set(d['idx'].tolist()) == set(range(8))
+
+
+def test_channel_remap_errors():
+    lib = _lib.load()
+    x = torch.zeros(2, 3, 21, device='cuda')
+    p = torch.zeros(2, 21, dtype=torch.int32, device='cuda')
+    s = torch.ones(2, 21, device='cuda')
+    assert lib.seld_channel_remap(_lib.ptr(x), 2, 3, 21, 1, _lib.ptr(p), _lib.ptr(s), None) == -4
+    assert lib.seld_channel_remap(None, 2, 3, 4, 1, _lib.ptr(p), _lib.ptr(s), None) == -1
+    assert lib.seld_channel_remap(_lib.ptr(x), 0, 3, 4, 1, _lib.ptr(p), _lib.ptr(s), None) == 0
+    with pytest.raises(ValueError):
+        T.foa_intensity_vec_aug(torch.zeros(1, 2, 3, 6), torch.zeros(1, 2, 12))
