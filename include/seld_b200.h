@@ -175,14 +175,15 @@ SELD_API int seld_mask(void* x_dev, int dtype, int64_t n_samples, int64_t t, int
               const int64_t* op_seed2_dev, int32_t* draws_out_dev, void* stream);
 
 /*
- * Per-sample channel gather + sign flip, in place: the data movement of the reference's batch-level spatial
- * augmentations (foa_intensity_vec_aug transforms.py:78-114, acs_aug :155-199).  x_dev is viewed as float32
- * [n_samples][outer][n_chan][inner]:  x[b, o, c, j] <- sign[b, c] * x[b, o, perm[b, c], j].
+ * Per-sample channel gather + sign flip, out of place: the data movement of the reference's batch-level spatial
+ * augmentations (foa_intensity_vec_aug transforms.py:78-114, acs_aug :155-199).  in/out are float32
+ * [n_samples][outer][n_chan][inner]:  out[b, o, c, j] = (table[b, c] < 0 ? -1 : 1) * in[b, o, table[b, c] & 0xff, j].
  * Features [B, T, F, C]: outer = T*F, inner = 1.  Label coordinates [B, T, 4, n_classes]: outer = T, n_chan = 4,
- * inner = n_classes.  perm_dev int32 [n_samples][n_chan], sign_dev float32 [n_samples][n_chan]; n_chan <= 20.
+ * inner = n_classes.  table_dev int32 [n_samples][n_chan] (source channel in the low byte, bit 31 = negate);
+ * n_chan <= 32, n_samples <= 65535, fewer than 2^31 elements per sample, in_dev != out_dev.
  */
-SELD_API int seld_channel_remap(float* x_dev, int64_t n_samples, int64_t outer, int n_chan, int64_t inner, const int32_t* perm_dev,
-                                const float* sign_dev, void* stream);
+SELD_API int seld_channel_remap(const float* in_dev, float* out_dev, int64_t n_samples, int64_t outer, int n_chan, int64_t inner,
+                                const int32_t* table_dev, void* stream);
 
 /*
  * Stand-alone stages (API parity with the reference's public helpers; the hot path is seld_extract).

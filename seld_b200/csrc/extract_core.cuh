@@ -435,8 +435,11 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
     // fully unrolled: measured 12% faster than a x2-rolled loop despite the larger instruction footprint
 #pragma unroll
     for (int i = 0; i < G::BPT; ++i) {
+        // bins past F-1 carry zero weights; they read their own (in-range, finite) slots of the full spectrum rather than a
+        // clamped index, which keeps the lane -> bank map of the last lanes conflict-free (32 * BPT <= N)
+        static_assert(32 * G::BPT <= N, "bin ownership must stay inside the spectrum buffer");
         const bool valid = kbeg + i < G::F;
-        const int k = valid ? kbeg + i : G::F - 1;       // bins past F-1 carry zero weights: recompute the last bin
+        const int k = kbeg + i;
         const int kn = (N - k) & (N - 1);
         const float2 z0 = S0[k], z0n = S0[kn], z1 = S1[k], z1n = S1[kn];
         float2 ch[4];                                  // twice the channel spectra

@@ -196,51 +196,46 @@ extern "C" int seld_mask(void* x_dev, int dtype, int64_t n_samples, int64_t t, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Per-sample channel gather + sign flip, in place: the data movement of the reference's batch-level spatial
-// augmentations (foa_intensity_vec_aug transforms.py:78-114, acs_aug :155-199), which only permute / negate channels of
-// the features [B, T, F, C] and of the label coordinates [B, T, 4, n_classes].  x is viewed as [n][outer][C][inner]:
-//     x[b, o, c, j] <- sign[b, c] * x[b, o, perm[b, c], j]
+// Per-sample channel gather + sign flip: the data movement of the reference's batch-level spatial augmentations
+// (foa_intensity_vec_aug transforms.py:78-114, acs_aug :155-199), which only permute / negate channels of the features
+// [B, T, F, C] and of the label coordinates [B, T, 4, n_classes].  With x viewed as [n][outer][C][inner]:
+//     out[b, o, c, j] = (table[b, c] < 0 ? -1 : 1) * in[b, o, table[b, c] & 0xff, j]
+// One thread per output element (coalesced stores; the C sources of a position share one or two cache lines), the
+// sample on blockIdx.y so the per-sample table sits in shared memory and all index arithmetic is 32-bit.
 namespace seld {
-template <int MAXC>
-__global__ void __launch_bounds__(256) channel_remap_kernel(float* __restrict__ x, long long n_samples, long long outer, int C,
-                                                            long long inner, const int* __restrict__ perm,
-                                                            const float* __restrict__ sign) {
-    const long long per_sample = outer * inner;
-    const long long total = n_samples * per_sample;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const long long b = i / per_sample, r = i - b * per_sample;
-        const long long o = r / inner, j = r - o * inner;
-        float* p = x + ((b * outer + o) * C) * inner + j;
-        float v[MAXC];
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) v[c] = (c < C) ? p[(long long)c * inner] : 0.f;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-            if (c < C) {
-                const int src = perm[b * C + c];
-                float val = 0.f;
-#pragma unroll
-                for (int s = 0; s < MAXC; ++s) val = (s == src) ? v[s] : val;          // register select, no local memory
-                p[(long long)c * inner] = sign[b * C + c] * val;
-            }
-        }
+__global__ void __launch_bounds__(256) channel_remap_kernel(const float* __restrict__ in, float* __restrict__ out, unsigned per_sample,
+                                                            unsigned C, unsigned inner, const int* __restrict__ table) {
+    __shared__ int s_tab[32];
+    const long long b = blockIdx.y;
+    if (threadIdx.x < C) s_tab[threadIdx.x] = table[b * C + threadIdx.x];
+    __syncthreads();
+    const float* src = in + b * per_sample;
+    float* dst = out + b * per_sample;
+    const unsigned ci = C * inner;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < per_sample; e += gridDim.x * blockDim.x) {
+        const unsigned o = e / ci, r = e - o * ci;
+        const unsigned c = r / inner, j = r - c * inner;
+        const int t = s_tab[c];
+        const float v = src[o * ci + unsigned(t & 0xff) * inner + j];
+        dst[e] = (t < 0 ? -1.0f : 1.0f) * v;
     }
 }
 }  // namespace seld
 
-extern "C" int seld_channel_remap(float* x_dev, int64_t n_samples, int64_t outer, int n_chan, int64_t inner, const int32_t* perm_dev,
-                                  const float* sign_dev, void* stream) {
-    if (!x_dev || !perm_dev || !sign_dev || n_samples < 0 || outer < 0 || inner < 1 || n_chan < 1) { set_error("bad argument"); return SELD_EINVAL; }
-    if (n_chan > 20) { set_error("at most 20 channels"); return SELD_EUNSUPPORTED; }
-    const long long total = n_samples * outer * inner;
-    if (total == 0) return SELD_OK;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (n_chan <= 4) channel_remap_kernel<4><<<(int)blocks, 256, 0, st>>>(x_dev, n_samples, outer, n_chan, inner, perm_dev, sign_dev);
-    else if (n_chan <= 10) channel_remap_kernel<10><<<(int)blocks, 256, 0, st>>>(x_dev, n_samples, outer, n_chan, inner, perm_dev, sign_dev);
-    else channel_remap_kernel<20><<<(int)blocks, 256, 0, st>>>(x_dev, n_samples, outer, n_chan, inner, perm_dev, sign_dev);
+extern "C" int seld_channel_remap(const float* in_dev, float* out_dev, int64_t n_samples, int64_t outer, int n_chan, int64_t inner,
+                                  const int32_t* table_dev, void* stream) {
+    if (!in_dev || !out_dev || !table_dev || n_samples < 0 || outer < 0 || inner < 1 || n_chan < 1) { set_error("bad argument"); return SELD_EINVAL; }
+    if (in_dev == out_dev) { set_error("seld_channel_remap is out of place"); return SELD_EINVAL; }
+    if (n_chan > 32) { set_error("at most 32 channels"); return SELD_EUNSUPPORTED; }
+    const long long per_sample = outer * n_chan * inner;
+    if (per_sample >= (1ll << 31) || n_samples > 65535) { set_error("sample too large (2^31 elements) or more than 65535 samples"); return SELD_EUNSUPPORTED; }
+    if (per_sample == 0 || n_samples == 0) return SELD_OK;
+    long long bx = (per_sample + 255) / 256;
+    const long long cap = (148ll * 16 + n_samples - 1) / n_samples;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    dim3 grid((unsigned)bx, (unsigned)n_samples);
+    channel_remap_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_dev, out_dev, (unsigned)per_sample, (unsigned)n_chan,
+                                                                            (unsigned)inner, table_dev);
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;
 }

@@ -207,13 +207,25 @@ def mic_gcc_perm(mic_perm):
     return torch.from_numpy(out) if isinstance(mic_perm, torch.Tensor) else out
 
 
-def _remap_(t, outer, n_chan, inner, perm, sign):
-    """x[b, o, c, j] <- sign[b, c] * x[b, o, perm[b, c], j] in place on a contiguous float32 CUDA tensor."""
-    perm_d = torch.as_tensor(np.ascontiguousarray(perm, dtype=np.int32), device=t.device)
-    sign_d = torch.as_tensor(np.ascontiguousarray(sign, dtype=np.float32), device=t.device)
-    with torch.cuda.device(t.device):
-        _lib.check(_lib.load().seld_channel_remap(_lib.ptr(t), t.shape[0], outer, n_chan, inner, _lib.ptr(perm_d),
-                                                  _lib.ptr(sign_d), _lib.current_stream_ptr()))
+def _pack_table(perm, sign):
+    """[B, C] source channels + signs (+1 / -1) -> int32 table of seld_channel_remap (bit 31 = negate)."""
+    t = np.asarray(perm, dtype=np.int64) | np.where(np.asarray(sign) < 0, 1 << 31, 0)
+    return t.astype(np.uint32).view(np.int32)
+
+
+def _remap_pair(xs, ys, x_tab, y_tab):
+    """Apply the per-sample tables to features [B, ..., C] and label coordinates [B, T, 4 * n_classes]; new tensors."""
+    b, cx = xs.shape[0], xs.shape[-1]
+    n_cls = ys.shape[-1] // 4
+    tab = torch.as_tensor(np.ascontiguousarray(np.concatenate([x_tab.ravel(), y_tab.ravel()])), device=xs.device)   # one H2D
+    xo, yo = torch.empty_like(xs), torch.empty_like(ys)
+    lib = _lib.load()
+    with torch.cuda.device(xs.device):
+        st = _lib.current_stream_ptr()
+        _lib.check(lib.seld_channel_remap(_lib.ptr(xs), _lib.ptr(xo), b, int(np.prod(xs.shape[1:-1])), cx, 1, tab.data_ptr(), st))
+        _lib.check(lib.seld_channel_remap(_lib.ptr(ys), _lib.ptr(yo), b, int(np.prod(ys.shape[1:-1])), 4, n_cls,
+                                          tab.data_ptr() + 4 * b * cx, st))
+    return xo, yo
 
 
 def _aug_inputs(x, y):
@@ -221,10 +233,6 @@ def _aug_inputs(x, y):
     dev = torch.device('cuda', torch.cuda.current_device())
     xs = torch.as_tensor(x).to(device=dev, dtype=torch.float32).contiguous()
     ys = torch.as_tensor(y).to(device=dev, dtype=torch.float32).contiguous()
-    if xs.data_ptr() == (x.data_ptr() if isinstance(x, torch.Tensor) else 0):
-        xs = xs.clone()                                  # the reference returns new tensors (tf.identity)
-    if ys.data_ptr() == (y.data_ptr() if isinstance(y, torch.Tensor) else 0):
-        ys = ys.clone()
     return xs, ys
 
 
@@ -262,9 +270,7 @@ def foa_intensity_vec_aug(x, y, seed=None, sample_offset=None, return_draws=Fals
     y_sign = np.ones((b, 4))
     y_perm[:, 1:4] = 1 + feat_perm                                       # label x, y, z                   (:107)
     y_sign[:, 1:4] = np.take_along_axis(sgn, feat_perm, 1)
-    _remap_(xs, int(np.prod(xs.shape[1:-1])), 7, 1, x_perm, x_sign)
-    n_cls = ys.shape[-1] // 4
-    _remap_(ys, int(np.prod(ys.shape[1:-1])), 4, n_cls, y_perm, y_sign)
+    xs, ys = _remap_pair(xs, ys, _pack_table(x_perm, x_sign), _pack_table(y_perm, y_sign))
     return (xs, ys, {'flip': flip, 'swap': swap}) if return_draws else (xs, ys)
 
 
@@ -298,7 +304,5 @@ def acs_aug(x, y, seed=None, sample_offset=None, return_draws=False):
     y_sign = np.ones((b, 4))
     y_perm[:, 1:4] = 1 + feat_perm                                       # (:183)
     y_sign[:, 1:4] = foa_sign
-    _remap_(xs, int(np.prod(xs.shape[1:-1])), 17, 1, x_perm, x_sign)
-    n_cls = ys.shape[-1] // 4
-    _remap_(ys, int(np.prod(ys.shape[1:-1])), 4, n_cls, y_perm, y_sign)
+    xs, ys = _remap_pair(xs, ys, _pack_table(x_perm, x_sign), _pack_table(y_perm, y_sign))
     return (xs, ys, {'idx': idx}) if return_draws else (xs, ys)

@@ -53,11 +53,12 @@ def test_acs_aug_matches_oracle(shape_x, shape_y):
 
 def test_channel_remap_errors():
     lib = _lib.load()
-    x = torch.zeros(2, 3, 21, device='cuda')
-    p = torch.zeros(2, 21, dtype=torch.int32, device='cuda')
-    s = torch.ones(2, 21, device='cuda')
-    assert lib.seld_channel_remap(_lib.ptr(x), 2, 3, 21, 1, _lib.ptr(p), _lib.ptr(s), None) == -4
-    assert lib.seld_channel_remap(None, 2, 3, 4, 1, _lib.ptr(p), _lib.ptr(s), None) == -1
-    assert lib.seld_channel_remap(_lib.ptr(x), 0, 3, 4, 1, _lib.ptr(p), _lib.ptr(s), None) == 0
+    x = torch.zeros(2, 3, 33, device='cuda')
+    o = torch.zeros_like(x)
+    p = torch.zeros(2, 33, dtype=torch.int32, device='cuda')
+    assert lib.seld_channel_remap(_lib.ptr(x), _lib.ptr(o), 2, 3, 33, 1, _lib.ptr(p), None) == -4
+    assert lib.seld_channel_remap(_lib.ptr(x), _lib.ptr(x), 2, 3, 4, 1, _lib.ptr(p), None) == -1      # out of place only
+    assert lib.seld_channel_remap(None, _lib.ptr(o), 2, 3, 4, 1, _lib.ptr(p), None) == -1
+    assert lib.seld_channel_remap(_lib.ptr(x), _lib.ptr(o), 0, 3, 4, 1, _lib.ptr(p), None) == 0
     with pytest.raises(ValueError):
         T.foa_intensity_vec_aug(torch.zeros(1, 2, 3, 6), torch.zeros(1, 2, 12))

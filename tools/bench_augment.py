@@ -1,5 +1,8 @@
 """Time the batch-level spatial augmentations on the reference's batch shape (train.py:163-165: [256, 300, 64, 7])."""
 import json
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from seld_b200 import transforms as T
 
