@@ -60,18 +60,18 @@ struct ExtractArgs {
     const int* piece0;
     const int* pb;
     int hop, n_mels;
-    int e_bytes;              // per-warp exchange / piece buffer size
-    int gather_unrolled;      // every mel segment has <= 3 pieces and n_mels <= 64: gather_pairs
+    int e_bytes;              // per-team piece / GCC exchange buffer size
+    int gather_unrolled;      // every mel segment has <= GATHER_MAXP pieces and n_mels <= 64: gather_lanes
     int gcc_tc;               // MIC: write fp16 pair phasors to gcc_rows; the tensor-core GEMM does the lag projection
     int t_g;                  // frames per clip that have a stored row (min(t_raw, t_out))
     float* gcc_rows;          // tile-blocked fp16 pair phasors, A operand of gcc_gemm (21 frames = 126 rows per tile)
     float* gcc_logmel;        // [n_clips * t_g][n_mels][4] un-clamped log-mel; gcc_gemm assembles the complete rows
     int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
     int origin;               // frame t starts at sample t*hop - n_fft/2 + origin (0: centred STFT; n_fft/2: uncentred chunks)
-    int fpw;                  // frames per warp per super-chunk
+    int fpw;                  // consecutive frames per team per super-chunk
     int assign_blocked;       // 0: super-chunk sc -> CTA sc mod grid; 1: each CTA walks one contiguous range
-    int fsc;                  // frames per super-chunk (<= warps * fpw); odd => CTA start phases cover all 128 B offsets
-    long long n_super;        // super-chunks of warps_per_cta * fpw frames
+    int fsc;                  // frames per super-chunk (teams * fpw)
+    long long n_super;        // super-chunks of fsc frames
 };
 
 static int frames_per_warp() {   // frames a warp handles per super-chunk (SELD_FPW overrides, for experiments)
@@ -86,18 +86,23 @@ __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 template <int R, int MODE>
 __host__ __device__ constexpr int table_bytes(int n_mels) {
     using G = Geo<R>;
-    return align16(G::N * 8) + align16(32 * G::BPT * 8) + align16(32 * 8) + align16(32 * 4) + align16((n_mels + 2) * 4) + 64 +
-           (MODE == MODE_MIC ? align16(G::N * 8) : 0);
+    return align16(G::N * 8) + align16(G::TL * G::BPT * 8) + align16(G::TL * 8) + align16(G::TL * 4) + align16((n_mels + 2) * 4) + 64 +
+           align16(G::N * 4) + (MODE == MODE_MIC ? align16(G::N * 8) : 0);
 }
+// One frame team (two warps): an exchange buffer per warp (its spectrum overwrites it in place), the piece / GCC exchange
+// buffer, and the staged output row.
 template <int R, int MODE>
-__host__ __device__ constexpr int warp_bytes(int n_mels, int e_bytes) {
+__host__ __device__ constexpr int team_bytes(int n_mels, int e_bytes) {
     using G = Geo<R>;
-    return e_bytes + 2 * align16(G::N * 8) + align16(n_mels * (MODE == MODE_FOA ? 7 : 10) * 4);
+    return 2 * align16(G::E_ELEMS * 8) + e_bytes + align16(n_mels * (MODE == MODE_FOA ? 7 : 10) * 4);
 }
 
-// register budget follows from the CTA size shared memory allows: 16 warps for n_fft <= 512, 8 for 1024, 4 for 2048
+// Warps per CTA.  n_fft = 1024: 12 warps = 6 teams (168 registers per thread; three warps per scheduler hide the
+// shared-memory and dependent-issue latency that two could not -- measured 2 -> 4 -> 8 warps: 35 -> 17.7 -> 11.5 ms).
 template <int R>
-__host__ __device__ constexpr int max_warps() { return R <= 16 ? 16 : (R == 32 ? 8 : 4); }
+__host__ __device__ constexpr int max_warps() { return R <= 16 ? 16 : (R == 32 ? 12 : 4); }
+
+__device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
 
 // EDGE = false: interior frames only, loads specialised on LAYOUT (the hot kernel).
 // EDGE = true : the few frames per clip that need reflection, plus the zero padding rows (generic strided loads).
@@ -105,42 +110,48 @@ template <int R, int MODE, int LAYOUT, bool EDGE, bool TC>
 __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(ExtractArgs a) {
     using G = Geo<R>;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
+    constexpr int TL = G::TL;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
+    const int h = warp & 1;                   // which channel pair this warp transforms
+    const int team = warp >> 1;
+    const int u = h * 32 + lane;              // lane within the team
+    const int bar_id = 1 + team;              // named barrier of the team (0 is __syncthreads)
 
     // ---- CTA-shared tables
     unsigned char* p = smem;
     float2* s_tw_t = reinterpret_cast<float2*>(p);  p += align16(G::N * 8);
-    float2* s_w01 = reinterpret_cast<float2*>(p);  p += align16(32 * G::BPT * 8);
-    unsigned long long* s_endmask = reinterpret_cast<unsigned long long*>(p);  p += align16(32 * 8);
-    int* s_piece0 = reinterpret_cast<int*>(p);  p += align16(32 * 4);
+    float2* s_w01 = reinterpret_cast<float2*>(p);  p += align16(TL * G::BPT * 8);
+    unsigned long long* s_endmask = reinterpret_cast<unsigned long long*>(p);  p += align16(TL * 8);
+    int* s_piece0 = reinterpret_cast<int*>(p);  p += align16(TL * 4);
     int* s_pb = reinterpret_cast<int*>(p);  p += align16((a.n_mels + 2) * 4);
     float2* s_zero = reinterpret_cast<float2*>(p);  p += 64;
+    float* s_win = reinterpret_cast<float*>(p);  p += align16(G::N * 4);
     float2* s_tw_lin = nullptr;
     if constexpr (MODE == MODE_MIC) { s_tw_lin = reinterpret_cast<float2*>(p);  p += align16(G::N * 8); }
+    const float wscale = ((EDGE ? a.layout : LAYOUT) == LAYOUT_PCM16_LC) ? (1.0f / 32768.0f) : 1.0f;    // exact: folds the PCM decode
     for (int i = threadIdx.x; i < G::N; i += blockDim.x) {
+        s_win[i] = a.window[i] * wscale;
         s_tw_t[i] = a.tw_t[i];
         if constexpr (MODE == MODE_MIC) s_tw_lin[i] = a.tw_lin[i];
     }
-    for (int i = threadIdx.x; i < 32 * G::BPT; i += blockDim.x) s_w01[i] = a.w01[i];
+    for (int i = threadIdx.x; i < TL * G::BPT; i += blockDim.x) s_w01[i] = a.w01[i];
     for (int i = threadIdx.x; i < a.n_mels + 2; i += blockDim.x) s_pb[i] = a.pb[i];
-    if (threadIdx.x < 32) { s_endmask[threadIdx.x] = a.endmask[threadIdx.x]; s_piece0[threadIdx.x] = a.piece0[threadIdx.x]; }
+    if (threadIdx.x < TL) { s_endmask[threadIdx.x] = a.endmask[threadIdx.x]; s_piece0[threadIdx.x] = a.piece0[threadIdx.x]; }
     if (threadIdx.x < 8) s_zero[threadIdx.x] = make_float2(0.f, 0.f);
-    // ---- per-warp regions
-    const int wbytes = warp_bytes<R, MODE>(a.n_mels, a.e_bytes);
-    unsigned char* wp = p + size_t(warp) * wbytes;
-    float2* E = reinterpret_cast<float2*>(wp);  wp += a.e_bytes;          // exchange buffer, then mel pieces
-    float2* S0 = reinterpret_cast<float2*>(wp);  wp += align16(G::N * 8);
-    float2* S1 = reinterpret_cast<float2*>(wp);  wp += align16(G::N * 8);
-    float* acc = reinterpret_cast<float*>(wp);
+    // ---- per-team regions
+    unsigned char* tp = p + size_t(team) * team_bytes<R, MODE>(a.n_mels, a.e_bytes);
+    float2* S0 = reinterpret_cast<float2*>(tp);  tp += align16(G::E_ELEMS * 8);     // warp 0: exchange, then spectrum of pair 0
+    float2* S1 = reinterpret_cast<float2*>(tp);  tp += align16(G::E_ELEMS * 8);     // warp 1: exchange, then spectrum of pair 1
+    float2* X = reinterpret_cast<float2*>(tp);  tp += a.e_bytes;                    // mel pieces, then GCC exchange
+    float* acc = reinterpret_cast<float*>(tp);
+    float2* E = h ? S1 : S0;
     const int row_elems = a.n_mels * C;
-    // ---- this lane's window taps stay in registers for the whole kernel
-    float wreg[R];
-#pragma unroll
-    for (int n2 = 0; n2 < R; ++n2) wreg[n2] = a.window[lane + 32 * n2] * ((EDGE ? a.layout : LAYOUT) == LAYOUT_PCM16_LC ? (1.0f / 32768.0f) : 1.0f);
     __syncthreads();
+    // window taps of this lane: s_win[lane + 32 n2].  The interior kernel reads them from shared memory per frame (at 168
+    // registers per thread a register copy would be spilled to local memory anyway); the edge kernel keeps a copy.
+    const float* wlane = s_win + lane;
 
     const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_piece0, s_pb, s_zero};
     const long long total_frames = (long long)a.n_clips * a.frames_per_clip;
@@ -148,37 +159,40 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     float run_max = -INFINITY;
     int run_clip = -1;
 
-    // everything after the two packed FFTs of a frame: mel pieces, gather, (GCC), row store, running clip maximum
+    // everything after the team's two packed FFTs: mel pieces, gather, (GCC), row store, running clip maximum
     auto finish_frame = [&](int clip, int t, float* row) {
         constexpr bool tc = TC && MODE == MODE_MIC && R == 32;       // tensor-core GCC: this kernel only writes phasor rows
-        bin_phase<R, MODE, tc>(S0, S1, tb, E, 1e-8f, lane);
-        __syncwarp();
-        float mx = a.gather_unrolled ? gather_pairs<MODE>(E, tb, acc, a.n_mels, lane)
-                                     : gather_phase<MODE, 0>(E, tb, acc, a.n_mels, lane);
-        __syncwarp();
+        team_bar(bar_id);                                            // both spectra are in place
+        bin_phase<R, MODE, tc>(S0, S1, tb, X, 1e-8f, u);
+        team_bar(bar_id);
+        float mx = a.gather_unrolled ? gather_lanes<MODE>(X, tb, acc, a.n_mels, u)
+                                     : gather_phase<MODE, 0>(X, tb, acc, a.n_mels, u);
+        if constexpr (MODE == MODE_MIC && !tc) {
+            team_bar(bar_id);                                        // pieces consumed: X is the GCC exchange buffer now
+            if (h == 0) {
+                gcc_stage1<R, 0>(S0, S1, X, lane);
+                __syncwarp();
+                gcc_stage2<R, 0>(X, tb, acc, a.n_mels, lane);
+                __syncwarp();
+                gcc_stage1<R, 1>(S0, S1, X, lane);
+                __syncwarp();
+                gcc_stage2<R, 1>(X, tb, acc, a.n_mels, lane);
+                __syncwarp();
+                gcc_stage1<R, 2>(S0, S1, X, lane);
+                __syncwarp();
+                gcc_stage2<R, 2>(X, tb, acc, a.n_mels, lane);
+            }
+        }
+        team_bar(bar_id);                                            // the row is complete
         if constexpr (tc) {
             if (t < a.t_g) {
                 const long long frame = (long long)clip * a.t_g + t;
-                gcc_tc_copy_out(S0, S1, a.gcc_rows, (frame / 21) * 128 + (frame % 21) * 6, lane);
+                gcc_tc_copy_out(S0, S1, a.gcc_rows, (frame / 21) * 128 + (frame % 21) * 6, lane, h ? 2 : 0, h ? 3 : 2);
                 float* lm = a.gcc_logmel + frame * (a.n_mels * 4);     // log-mel only; gcc_gemm writes the feature row
-                for (int e = lane; e < a.n_mels * 4; e += 32) lm[e] = acc[(e >> 2) * C + (e & 3)];
+                for (int e = u; e < a.n_mels * 4; e += TL) lm[e] = acc[(e >> 2) * C + (e & 3)];
             }
         }
-        if constexpr (MODE == MODE_MIC && !tc) {
-            gcc_stage1<R, 0>(S0, S1, E, lane);
-            __syncwarp();
-            gcc_stage2<R, 0>(E, tb, acc, a.n_mels, lane);
-            __syncwarp();
-            gcc_stage1<R, 1>(S0, S1, E, lane);
-            __syncwarp();
-            gcc_stage2<R, 1>(E, tb, acc, a.n_mels, lane);
-            __syncwarp();
-            gcc_stage1<R, 2>(S0, S1, E, lane);
-            __syncwarp();
-            gcc_stage2<R, 2>(E, tb, acc, a.n_mels, lane);
-            __syncwarp();
-        }
-        if (!tc && row != nullptr) store_row(acc, row_elems, row, lane);
+        if (!tc && row != nullptr) store_row(acc, row_elems, row, u, TL);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if (clip != run_clip) {
@@ -187,13 +201,12 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
             run_max = -INFINITY;
         }
         run_max = fmaxf(run_max, mx);
-        __syncwarp();
     };
 
     if constexpr (EDGE) {
         for (long long sc = blockIdx.x; sc < a.n_super; sc += gridDim.x) {
-            const long long g0 = sc * a.fsc + warp * a.fpw;
-            for (int i = 0; i < a.fpw && warp * a.fpw + i < a.fsc; ++i) {
+            const long long g0 = sc * a.fsc + team * a.fpw;
+            for (int i = 0; i < a.fpw && team * a.fpw + i < a.fsc; ++i) {
                 const long long g = g0 + i;
                 if (g >= total_frames) break;
                 const int clip = int(g / a.frames_per_clip);
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
                 const int t = (j < a.t_lo) ? j : a.t_hi + (j - a.t_lo);
                 float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
                 if (t >= a.t_raw) {                   // zero padding rows (reference :142-145)
-                    for (int e = lane; e < row_elems; e += 32) row[e] = 0.f;
+                    for (int e = u; e < row_elems; e += TL) row[e] = 0.f;
                     continue;
                 }
                 ClipSrc src;
@@ -210,88 +223,72 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
                 if (a.layout == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
                 else { src.chan_stride = 1; src.samp_stride = 4; }
                 const long long start = (long long)t * a.hop - G::N / 2 + a.origin;
-#pragma unroll 1
-                for (int pr = 0; pr < 2; ++pr) {
+                {
+                    float wreg[R];
+#pragma unroll
+                    for (int n2 = 0; n2 < R; ++n2) wreg[n2] = wlane[32 * n2];
                     float2 v[R];
                     if (a.layout == LAYOUT_PCM16_LC)
                         stage1_load_reflect_pcm16<R>(reinterpret_cast<const short*>(a.wav) + (long long)clip * 4 * a.n_samples,
-                                                     a.n_samples, pr, start, wreg, v, lane);
+                                                     a.n_samples, h, start, wreg, v, lane);
                     else
-                        stage1_load_reflect<R>(src, 2 * pr, 2 * pr + 1, start, wreg, v, lane);
+                        stage1_load_reflect<R>(src, 2 * h, 2 * h + 1, start, wreg, v, lane);
                     stage1_fft_store<R>(v, tb, E, lane);
-                    __syncwarp();
-                    stage2_forward<R>(E, pr ? S1 : S0, lane);
-                    __syncwarp();
                 }
+                __syncwarp();
+                stage2_forward<R>(E, E, lane);
                 finish_frame(clip, t, row);
             }
         }
     } else {
-        // Interior frames, software-pipelined over half-frames (one channel pair each): the raw samples of the NEXT
-        // half-frame are requested before the current one's FFT starts, so HBM/L2 latency hides behind the arithmetic.
+        // Interior frames, software-pipelined: the raw samples of the team's NEXT frame (this warp's channel pair) are
+        // requested before the current frame's FFT starts, so HBM/L2 latency hides behind the arithmetic (requesting them
+        // later -- after the bin phase -- measured 6 % slower).
         const long long sc_step = a.assign_blocked ? 1 : gridDim.x;
         const long long per_cta = (a.n_super + gridDim.x - 1) / gridDim.x;
         long long sc = a.assign_blocked ? blockIdx.x * per_cta : blockIdx.x;
         const long long sc_end = a.assign_blocked ? (sc + per_cta < a.n_super ? sc + per_cta : a.n_super) : a.n_super;
         int fi = 0;
         auto frame_index = [&](long long s, int i) -> long long {       // -1 past the end
-            if (s >= sc_end || warp * a.fpw + i >= a.fsc) return -1;
-            const long long g = s * a.fsc + warp * a.fpw + i;
+            if (s >= sc_end || team * a.fpw + i >= a.fsc) return -1;
+            const long long g = s * a.fsc + team * a.fpw + i;
             return g < total_frames ? g : -1;
         };
-        auto source_of = [&](long long g, ClipSrc& src, long long& start, int& clip, int& t) {
-            clip = int(g / a.frames_per_clip);
-            t = a.t_lo + int(g - (long long)clip * a.frames_per_clip);
-            src.base = a.wav + (long long)clip * 4 * a.n_samples;
-            src.n_samples = a.n_samples;
-            if constexpr (LAYOUT == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
-            else { src.chan_stride = 1; src.samp_stride = 4; }
-            start = (long long)t * a.hop - G::N / 2 + a.origin;
-        };
-        long long g = frame_index(sc, fi);
         float2 raw[R];
-        ClipSrc src;
         long long start = 0;
         int clip = 0, t = 0;
-        auto load_frame = [&](int pair) {           // PCM16: one load brings both pairs (issued for pair 0 only)
+        auto request = [&](long long g) {           // issue the loads of frame g (this warp's pair) into raw[]
+            clip = int(g / a.frames_per_clip);
+            t = a.t_lo + int(g - (long long)clip * a.frames_per_clip);
+            start = (long long)t * a.hop - G::N / 2 + a.origin;
             if constexpr (LAYOUT == LAYOUT_PCM16_LC) {
-                if (pair == 0)
-                    stage1_load_raw_pcm16<R>(reinterpret_cast<const short*>(a.wav) + (long long)clip * 4 * a.n_samples, start, raw, lane);
+                stage1_load_raw_pcm16_pair<R>(reinterpret_cast<const short*>(a.wav) + (long long)clip * 4 * a.n_samples, h, start, raw, lane);
             } else {
-                stage1_load_raw<R, LAYOUT>(src, 2 * pair, 2 * pair + 1, start, raw, lane);
+                ClipSrc src;
+                src.base = a.wav + (long long)clip * 4 * a.n_samples;
+                src.n_samples = a.n_samples;
+                if constexpr (LAYOUT == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
+                else { src.chan_stride = 1; src.samp_stride = 4; }
+                stage1_load_raw<R, LAYOUT>(src, 2 * h, 2 * h + 1, start, raw, lane);
             }
         };
-        if (g >= 0) {
-            source_of(g, src, start, clip, t);
-            load_frame(0);
-        }
-        int pr = 0;
+        long long g = frame_index(sc, fi);
+        if (g >= 0) request(g);
 #pragma unroll 1
         while (g >= 0) {
             float2 v[R];
-            if constexpr (LAYOUT == LAYOUT_PCM16_LC) apply_window_pcm16<R>(raw, pr, wreg, v);
-            else apply_window<R>(raw, wreg, v);
-            // request the next half-frame
-            long long g_next = g;
-            if (pr == 0) {
-                load_frame(1);
-            } else {
-                if (++fi == a.fpw || warp * a.fpw + fi >= a.fsc) { fi = 0; sc += sc_step; }
-                g_next = frame_index(sc, fi);
-            }
+            if constexpr (LAYOUT == LAYOUT_PCM16_LC) apply_window_pcm16<R, 32>(raw, 0, wlane, v);
+            else apply_window<R, 32>(raw, wlane, v);
             const int clip_now = clip, t_now = t;
             float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
-            if (pr == 1 && g_next >= 0) {
-                source_of(g_next, src, start, clip, t);
-                load_frame(0);
-            }
+            if (++fi == a.fpw || team * a.fpw + fi >= a.fsc) { fi = 0; sc += sc_step; }
+            const long long g_next = frame_index(sc, fi);
+            if (g_next >= 0) request(g_next);
             stage1_fft_store<R>(v, tb, E, lane);
             __syncwarp();
-            stage2_forward<R>(E, pr ? S1 : S0, lane);
-            __syncwarp();
-            if (pr == 1) finish_frame(clip_now, t_now, row);
+            stage2_forward<R>(E, E, lane);
+            finish_frame(clip_now, t_now, row);
             g = g_next;
-            pr ^= 1;
         }
     }
     if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], float_to_key(run_max));
@@ -308,7 +305,7 @@ static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream)
     if (a.frames_per_clip <= 0) return SELD_OK;
     a.fpw = frames_per_warp();
     a.assign_blocked = 0;
-    a.fsc = plan->warps_per_cta * a.fpw;
+    a.fsc = (plan->warps_per_cta / 2) * a.fpw;
     const long long per_super = a.fsc;
     a.n_super = ((long long)a.n_clips * a.frames_per_clip + per_super - 1) / per_super;
     long long grid = a.n_super < plan->grid ? a.n_super : plan->grid;
@@ -368,11 +365,15 @@ static void plan_geometry_mode(seld_plan* plan) {
     if (plan->n_pieces * pstride > e_bytes) e_bytes = align16(plan->n_pieces * pstride);
     plan->e_bytes = e_bytes;
     const int tb = table_bytes<R, MODE>(plan->n_mels);
-    const int wb = warp_bytes<R, MODE>(plan->n_mels, e_bytes);
-    int warps = (plan->max_smem_optin - tb) / wb;
+    const int wb = team_bytes<R, MODE>(plan->n_mels, e_bytes);
+    int warps = 2 * ((plan->max_smem_optin - tb) / wb);          // two warps per frame team
     if (warps > max_warps<R>()) warps = max_warps<R>();
+    if (const char* e = getenv("SELD_WARPS")) {           // experiments only: fewer warps per CTA
+        const int n = atoi(e);
+        if (n >= 2 && n < warps) warps = n & ~1;
+    }
     plan->warps_per_cta = warps;
-    plan->extract_smem_bytes = tb + warps * wb;
+    plan->extract_smem_bytes = tb + (warps / 2) * wb;
     plan->grid = plan->num_sms;
 }
 template <int R>
@@ -478,8 +479,8 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
         }
     up((void**)&plan->tw_t, twt.data(), sizeof(float) * 2 * n_fft);
     up((void**)&plan->w01, mp.w01.data(), sizeof(float) * mp.w01.size());
-    up((void**)&plan->endmask, mp.endmask.data(), sizeof(unsigned long long) * 32);
-    up((void**)&plan->piece0, mp.piece0.data(), sizeof(int) * 32);
+    up((void**)&plan->endmask, mp.endmask.data(), sizeof(unsigned long long) * mp.endmask.size());
+    up((void**)&plan->piece0, mp.piece0.data(), sizeof(int) * mp.piece0.size());
     up((void**)&plan->pb, mp.pb.data(), sizeof(int) * mp.pb.size());
     if (e != cudaSuccess) {
         seld_plan_destroy(plan);
@@ -604,7 +605,7 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
             a.gcc_logmel = a.gcc_rows + ((frames + 20) / 21) * 128 * 512;
         }
     }
-    a.gather_unrolled = plan->max_pieces_per_seg <= 3 && plan->n_mels <= 64;
+    a.gather_unrolled = plan->max_pieces_per_seg <= GATHER_MAXP && plan->n_mels <= 64;
     // frames [t_lo, t_hi) need no reflection: t*hop - n_fft/2 >= 0 and t*hop + n_fft/2 <= n_samples
     {
         const long long half = plan->n_fft / 2;

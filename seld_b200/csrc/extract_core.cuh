@@ -1,4 +1,5 @@
-// Per-warp phases of the fused SELD feature extractor (one warp = one STFT frame of 4 channels).
+// Per-lane phases of the fused SELD feature extractor.  A TEAM of two warps (TL = 64 lanes) owns one STFT frame of 4
+// channels: each warp transforms one packed channel pair, then all 64 lanes share the bin phase and the mel gather.
 //
 // Reference behaviour replaced (file:line relative to the reference repo):
 //   complex_spec            feature_extractor.py:153-173  (centred STFT, reflect pad, periodic Hann
@@ -13,14 +14,15 @@
 //            DIF FFT in registers (packed f32x2 butterflies: the kernel is issue-bound and FADD2/FFMA2
 //            do two FP32 lanes per issue slot); twiddle W_N^(lane*k2) from a lane-contiguous table;
 //            transposed through the warp's exchange buffer with 128-bit stores.
-//   stage 2  lane k2 runs a 32-point FFT down its column -> Z[R*k1 + k2] written to the spectrum buffer.
-//   bins     lane owns a contiguous run of bins k, splits Z[k], Z[N-k] into the two real channels'
+//   stage 2  lane k2 runs a 32-point FFT down its column -> Z[R*k1 + k2], written back IN PLACE over the exchange
+//            buffer (linear index) once every lane holds its column in registers.
+//   bins     team lane u (0..63) owns a contiguous run of bins k, splits Z[k], Z[N-k] into the two real channels'
 //            spectra, forms power / intensity vectors (or per-channel unit phasors), and reduces them
 //            into the mel accumulators (each bin feeds at most two adjacent filters).
 //   gcc      three packed Hermitian inverse transforms (two pairs each) pruned to the n_mels centre lags.
 //
 // Every function is per-lane and only communicates through the shared-memory pointers it is given, so
-// the same code runs lane-by-lane on the CPU in tests/emu (phase boundary == __syncwarp()).
+// the same code runs lane-by-lane on the CPU in tests/emu (phase boundary == __syncwarp() or the team barrier).
 #pragma once
 
 #include "seld_common.cuh"
@@ -37,11 +39,11 @@ struct Tables {             // CTA-shared constant tables (shared memory on the 
     const float* window;    // [N]      periodic Hann(win_length) zero-padded centred to N
     const float2* tw_t;     // [R][32]  tw_t[k2*32 + lane] = exp(-2 pi i lane*k2 / N)   (lane-contiguous)
     const float2* tw_lin;   // [N]      exp(-2 pi i j / N)  (generic GCC lags only; may be null otherwise)
-    // sparse mel bank in "piece" form (built by seld_plan_create): lane l owns bins [l*BPT, (l+1)*BPT); a piece is a
-    // maximal run of one lane's bins that feed the same pair of adjacent filters (seg, seg+1)
-    const float2* w01;          // [32*BPT] 0.25 * (weight into filter seg, weight into filter seg+1); 0 past bin F-1
-    const unsigned long long* endmask;  // [32] bit i set: bin l*BPT + i is the last bin of a piece
-    const int* piece0;          // [32]     index of lane l's first piece
+    // sparse mel bank in "piece" form (built by seld_plan_create): team lane u owns bins [u*BPT, (u+1)*BPT); a piece is
+    // a maximal run of one lane's bins that feed the same pair of adjacent filters (seg, seg+1)
+    const float2* w01;          // [TL*BPT] 0.25 * (weight into filter seg, weight into filter seg+1); 0 past bin F-1
+    const unsigned long long* endmask;  // [TL] bit i set: bin u*BPT + i is the last bin of a piece
+    const int* piece0;          // [TL]     index of lane u's first piece
     const int* pb;              // [n_mels + 2] pieces with seg == m are [pb[m+1], pb[m+2])
     const float2* zero_rec;     // [8] zeros: a piece record that contributes nothing
 };
@@ -60,7 +62,8 @@ struct Geo {
     static constexpr int EP = R + 2;                 // padded row of the exchange buffer: 128-bit stores conflict-free
     static constexpr int E_ELEMS = 32 * EP;          // float2 elements
     static constexpr int COLS = (R + 31) / 32;       // stage-2 columns per lane
-    static constexpr int BPT = (F + 31) / 32;        // bins per lane in the bin phase
+    static constexpr int TL = 64;                    // lanes of a frame team (two warps)
+    static constexpr int BPT = (F + TL - 1) / TL;    // bins per team lane in the bin phase
     static constexpr int LOG2R = ilog2(R);
 };
 
@@ -199,6 +202,14 @@ SELD_HD void stage1_load_raw_pcm16(const short* base, long long frame_start, flo
     for (int n2 = 0; n2 < R; ++n2) raw[n2] = p[32 * n2];
 }
 
+// One channel pair only (32-bit load per tap): the team's warp `pair` reads its half of every 8-byte sample.
+template <int R>
+SELD_HD void stage1_load_raw_pcm16_pair(const short* base, int pair, long long frame_start, float2* raw, int lane) {
+    const float* p = reinterpret_cast<const float*>(base + (frame_start + lane) * 4 + 2 * pair);
+#pragma unroll
+    for (int n2 = 0; n2 < R; ++n2) raw[n2].x = p[64 * n2];
+}
+
 SELD_HD float2 pcm16_pair_to_float(float packed) {       // two int16 in one 32-bit word -> (lo, hi) as floats
 #if defined(__CUDA_ARCH__)
     const unsigned w = __float_as_uint(packed);
@@ -211,11 +222,12 @@ SELD_HD float2 pcm16_pair_to_float(float packed) {       // two int16 in one 32-
 #endif
 }
 
-template <int R>
+// WS: stride of the window taps (1: a per-lane register array; 32: the shared table offset by the lane)
+template <int R, int WS = 1>
 SELD_HD void apply_window_pcm16(const float2* raw, int pair, const float* wreg16, float2* v) {
 #pragma unroll
     for (int n2 = 0; n2 < R; ++n2)
-        v[n2] = pmul(pcm16_pair_to_float(pair ? raw[n2].y : raw[n2].x), make_float2(wreg16[n2], wreg16[n2]));
+        v[n2] = pmul(pcm16_pair_to_float(pair ? raw[n2].y : raw[n2].x), make_float2(wreg16[n2 * WS], wreg16[n2 * WS]));
 }
 
 // edge frames of PCM16 input (reflection): plain conversions, same value as the interior path
@@ -236,10 +248,10 @@ SELD_HD void stage1_load_reflect_pcm16(const short* base, long long n_samples, i
     }
 }
 
-template <int R>
+template <int R, int WS = 1>
 SELD_HD void apply_window(const float2* raw, const float* wreg, float2* v) {
 #pragma unroll
-    for (int n2 = 0; n2 < R; ++n2) v[n2] = pmul(raw[n2], make_float2(wreg[n2], wreg[n2]));
+    for (int n2 = 0; n2 < R; ++n2) v[n2] = pmul(raw[n2], make_float2(wreg[n2 * WS], wreg[n2 * WS]));
 }
 
 template <int R, int LAYOUT>
@@ -299,22 +311,42 @@ SELD_HD void stage1_forward(const ClipSrc& src, int ch_a, int ch_b, long long fr
 }
 
 // ---------------------------------------------------------------- stage 2: 32-point FFT per column
+// Two per-lane phases so the spectrum can overwrite the exchange buffer (S == E is allowed): every lane first pulls
+// its column(s) into registers and transforms them; after a __syncwarp() the results go back at linear index k.
 template <int R>
-SELD_HD void stage2_forward(const float2* E, float2* S, int lane) {
+SELD_HD void stage2_load_fft(const float2* E, float2* u, int lane) {      // u[COLS * 32]
     using G = Geo<R>;
 #pragma unroll
     for (int c = 0; c < G::COLS; ++c) {
         const int k2 = lane + 32 * c;
         if (k2 < R) {
-            float2 u[32];
 #pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) u[n1] = E[n1 * G::EP + k2];
-            pfft_dif<32>(u);
-#pragma unroll
-            for (int p = 0; p < 32; ++p) S[R * bitrev(p, 5) + k2] = u[p];
+            for (int n1 = 0; n1 < 32; ++n1) u[32 * c + n1] = E[n1 * G::EP + k2];
+            pfft_dif<32>(u + 32 * c);
         }
     }
 }
+template <int R>
+SELD_HD void stage2_store(const float2* u, float2* S, int lane) {
+    using G = Geo<R>;
+#pragma unroll
+    for (int c = 0; c < G::COLS; ++c) {
+        const int k2 = lane + 32 * c;
+        if (k2 < R) {
+#pragma unroll
+            for (int p = 0; p < 32; ++p) S[R * bitrev(p, 5) + k2] = u[32 * c + p];
+        }
+    }
+}
+#if defined(__CUDACC__)
+template <int R>
+__device__ __forceinline__ void stage2_forward(const float2* E, float2* S, int lane) {
+    float2 u[Geo<R>::COLS * 32];
+    stage2_load_fft<R>(E, u, lane);
+    __syncwarp();
+    stage2_store<R>(u, S, lane);
+}
+#endif
 
 SELD_HD float rsqrt_ftz(float s) {      // one MUFU.RSQ; subnormal inputs flush to 0 -> +inf (callers clamp)
 #if defined(__CUDA_ARCH__)
@@ -344,7 +376,7 @@ SELD_HD float2 unit_phasor(float2 a) {   // a / |a|, (0,0) for a == 0; scaled so
 // written back in place of the packed spectra for the GCC phase).  With Z = FFT(a + i b):
 // 2 A[k] = Z[k] + conj(Z[N-k]), 2 B[k] = -i (Z[k] - conj(Z[N-k])); the factor 2 is carried: powers come out
 // 4x (the mel weights are pre-scaled by the exact constant 1/4) and the intensity vector, scale-free apart from
-// eps, is produced 4x as well.  Each lane walks its BPT contiguous bins in straight-line, branch-free code,
+// eps, is produced 4x as well.  Each team lane walks its BPT contiguous bins in straight-line, branch-free code,
 // accumulating (into filter seg, into filter seg+1) as one packed FFMA2 per channel; at the end of every piece the
 // pair sums are stored (predicated) as one record P[piece][c] = (sum w0 val_c, sum w1 val_c) and the accumulators
 // are cleared.  Records are PSTRIDE = 7 | 5 float2 apart: 14 | 10 words, so 16 neighbouring pieces hit 16 different
@@ -419,14 +451,14 @@ SELD_HD float pack_half2(float lo, float hi) {          // two floats -> one 32-
 // phasors exp(i angle(conj(X_m) X_n)) as fp16 (re, im) words into the bin's own four spectrum slots -- the A operand
 // rows of the tensor-core lag projection (gcc_gemm.cu), copied out by gcc_tc_copy_out.
 template <int R, int MODE, bool GCC_TC = false>
-SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, float eps, int lane) {
+SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, float eps, int u) {     // u: team lane, 0..TL-1
     using G = Geo<R>;
     constexpr int N = G::N;
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
-    const int kbeg = lane * G::BPT;
-    const unsigned long long endmask = tb.endmask[lane];
-    int piece = tb.piece0[lane];
+    const int kbeg = u * G::BPT;
+    const unsigned long long endmask = tb.endmask[u];
+    int piece = tb.piece0[u];
     float2 acc2[NV];
 #pragma unroll
     for (int c = 0; c < NV; ++c) acc2[c] = make_float2(0.f, 0.f);
@@ -436,8 +468,8 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
 #pragma unroll
     for (int i = 0; i < G::BPT; ++i) {
         // bins past F-1 carry zero weights; they read their own (in-range, finite) slots of the full spectrum rather than a
-        // clamped index, which keeps the lane -> bank map of the last lanes conflict-free (32 * BPT <= N)
-        static_assert(32 * G::BPT <= N, "bin ownership must stay inside the spectrum buffer");
+        // clamped index, which keeps the lane -> bank map of the last lanes conflict-free (TL * BPT <= N)
+        static_assert(G::TL * G::BPT <= N, "bin ownership must stay inside the spectrum buffer");
         const bool valid = kbeg + i < G::F;
         const int k = kbeg + i;
         const int kn = (N - k) & (N - 1);
@@ -502,15 +534,15 @@ SELD_HD float fast_db(float x) {            // 10 log10(x), x > 0
 }
 
 // ---------------------------------------------------------------- gather: pieces -> mel rows
-// Lane l owns filters m = l, l + 32, ...: mel[m][c] = sum_{pieces of seg m} P.x + sum_{pieces of seg m-1} P.y, in piece
-// order.  Log-mel channels get 10 log10(max(., 1e-10)) here; returns the lane's maximum dB.
+// Team lane u owns filters m = u, u + TL, ...: mel[m][c] = sum_{pieces of seg m} P.x + sum_{pieces of seg m-1} P.y, in
+// piece order.  Log-mel channels get 10 log10(max(., 1e-10)) here; returns the lane's maximum dB.
 template <int MODE, int MAXP>
-SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_mels, int lane) {
+SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_mels, int u) {
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
     float mx = -INFINITY;
-    for (int m = lane; m < n_mels; m += 32) {
+    for (int m = u; m < n_mels; m += 64) {
         const int p0 = tb.pb[m], p1 = tb.pb[m + 1], p2 = tb.pb[m + 2];
         float sum[NV];
 #pragma unroll
@@ -555,73 +587,65 @@ SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_
     return mx;
 }
 
-// Fast gather for n_mels <= 64 and <= 3 pieces per segment: lane l totals the pieces of segments 2l and 2l+1 with
-// packed adds (missing pieces read an all-zero record), so mel[2l+1] = A[2l+1].x + A[2l].y stays inside the lane and
-// mel[2l] = A[2l].x + A[2l-1].y needs one shuffle from lane l-1 per channel.
+// Fast gather for n_mels <= TL and <= GATHER_MAXP pieces per segment: team lane u totals the pieces of segment u with
+// packed adds (missing pieces read an all-zero record); mel[u] = A[u].x + A[u-1].y takes one shuffle per channel from the
+// lane below -- lane 0 of the team's second warp re-totals segment u-1 itself (same additions in the same order, so the
+// CPU emulation, which always re-totals, is bit-identical).
+constexpr int GATHER_MAXP = 4;
+
 template <int MODE>
-SELD_HD float gather_pairs(const float2* P, const Tables& tb, float* acc, int n_mels, int lane
-#if !defined(__CUDA_ARCH__)
-                           , float2* xchg      // host emulation of the shuffle: [32][NV] (A[2l+1].y of every lane)
-#endif
-) {
+SELD_HD void seg_total(const float2* P, const Tables& tb, int seg, int n_mels, float2* A) {
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
-    constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
-    float2 A[2][NV];
+    const bool on = seg >= 0 && seg < n_mels;
+    const int ps = on ? tb.pb[seg + 1] : 0, pe = on ? tb.pb[seg + 2] : 0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int s = 2 * lane + h;
-        const int ps = (s < n_mels) ? tb.pb[s + 1] : 0, pe = (s < n_mels) ? tb.pb[s + 2] : 0;
+    for (int c = 0; c < NV; ++c) A[c] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < NV; ++c) A[h][c] = make_float2(0.f, 0.f);
+    for (int j = 0; j < GATHER_MAXP; ++j) {
+        const float2* rec = (ps + j < pe) ? P + (ps + j) * PSTRIDE : tb.zero_rec;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float2* rec = (ps + j < pe) ? P + (ps + j) * PSTRIDE : tb.zero_rec;
-#pragma unroll
-            for (int c = 0; c < NV; ++c) A[h][c] = padd(A[h][c], rec[c]);
-        }
+        for (int c = 0; c < NV; ++c) A[c] = padd(A[c], rec[c]);
     }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < NV; ++c) {
+}
+
+template <int MODE>
+SELD_HD float gather_lanes(const float2* P, const Tables& tb, float* acc, int n_mels, int u) {
+    constexpr int NV = PieceGeo<MODE>::NV;
+    constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
+    float2 A[NV];
+    seg_total<MODE>(P, tb, u, n_mels, A);
+    float below[NV];
 #if defined(__CUDA_ARCH__)
-        float below = __shfl_up_sync(0xffffffffu, A[1][c].y, 1);
+#pragma unroll
+    for (int c = 0; c < NV; ++c) below[c] = __shfl_up_sync(0xffffffffu, A[c].y, 1);
+    if ((u & 31) == 0) {
+        float2 B[NV];
+        seg_total<MODE>(P, tb, u - 1, n_mels, B);          // all zero for u == 0
+#pragma unroll
+        for (int c = 0; c < NV; ++c) below[c] = B[c].y;
+    }
 #else
-        float below = (lane > 0) ? xchg[(lane - 1) * NV + c].y : 0.f;
+    {
+        float2 B[NV];
+        seg_total<MODE>(P, tb, u - 1, n_mels, B);
+        for (int c = 0; c < NV; ++c) below[c] = B[c].y;
+    }
 #endif
-        if (lane == 0) below = 0.f;
-        float v0 = A[0][c].x + below;
-        float v1 = A[1][c].x + A[0][c].y;
-        if (c < 4) {
-            v0 = fast_db(fmaxf(v0, 1e-10f));
-            v1 = fast_db(fmaxf(v1, 1e-10f));
-            if (2 * lane < n_mels) mx = fmaxf(mx, v0);
-            if (2 * lane + 1 < n_mels) mx = fmaxf(mx, v1);
+    float mx = -INFINITY;
+    if (u < n_mels) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            float v = A[c].x + below[c];
+            if (c < 4) {
+                v = fast_db(fmaxf(v, 1e-10f));
+                mx = fmaxf(mx, v);
+            }
+            acc[u * C + c] = v;
         }
-        if (2 * lane < n_mels) acc[(2 * lane) * C + c] = v0;
-        if (2 * lane + 1 < n_mels) acc[(2 * lane + 1) * C + c] = v1;
     }
     return mx;
 }
-
-#if !defined(__CUDA_ARCH__)
-// host emulation helper: phase 1 of gather_pairs (what the shuffle would see)
-template <int MODE>
-inline void gather_pairs_publish(const float2* P, const Tables& tb, int n_mels, int lane, float2* xchg) {
-    constexpr int NV = PieceGeo<MODE>::NV;
-    constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
-    const int s = 2 * lane + 1;
-    const int ps = (s < n_mels) ? tb.pb[s + 1] : 0, pe = (s < n_mels) ? tb.pb[s + 2] : 0;
-    for (int c = 0; c < NV; ++c) {
-        float2 a = make_float2(0.f, 0.f);
-        for (int j = 0; j < 3; ++j) {
-            const float2* rec = (ps + j < pe) ? P + (ps + j) * PSTRIDE : tb.zero_rec;
-            a = padd(a, rec[c]);
-        }
-        xchg[lane * NV + c] = a;
-    }
-}
-#endif
 
 // ---------------------------------------------------------------- tensor-core GCC: copy the A rows out
 // rows: [6][512] 32-bit words (one fp16 (re, im) pair per bin; word 0 = (Re P[0], Re P[N/2])).  Lane l copies bins
@@ -631,14 +655,16 @@ inline void gather_pairs_publish(const float2* P, const Tables& tb, int n_mels, 
 // per (tile, chunk of 32 bins) one 16 KB block; row r of the chunk is 128 contiguous bytes at r * 128 and its 16-byte
 // unit u sits at unit position u ^ (r % 8).  Lane l holds bin k = l + 32 * chunk = word l of the row, so every store
 // instruction writes one full 128-byte line.  tile_row = tile * 128 + row-in-tile of the frame's first pair.
+// Slots pp in [pp_lo, pp_hi): the team's first warp copies slots 0 and 1 (both live in S0), the second slot 2 (S1).
 __device__ __forceinline__ void gcc_tc_copy_out(const float2* S0, const float2* S1, float* scratch, long long tile_row,
-                                                int lane) {
+                                                int lane, int pp_lo, int pp_hi) {
     constexpr int N = 1024;
     const long long tile = tile_row >> 7;
     const int r_first = int(tile_row & 127);
     float* tbase = scratch + tile * (16 * 4096);
 #pragma unroll
     for (int pp = 0; pp < 3; ++pp) {                 // slot pp holds pairs 2pp (.x) and 2pp + 1 (.y)
+        if (pp < pp_lo || pp >= pp_hi) continue;
         const int ra = r_first + 2 * pp, rb = ra + 1;
         float* dst0 = tbase + ra * 32 + ((((lane >> 2) ^ (ra & 7)) << 2) | (lane & 3));
         float* dst1 = tbase + rb * 32 + ((((lane >> 2) ^ (rb & 7)) << 2) | (lane & 3));
@@ -761,13 +787,13 @@ SELD_HD void gcc_stage2(const float2* E, const Tables& tb, float* acc, int n_mel
 
 // ---------------------------------------------------------------- finish one frame row
 // Coalesced copy of the staged row acc[m * C + c] to global memory.
-SELD_HD void store_row(const float* acc, int row_elems, float* out_row, int lane) {
+SELD_HD void store_row(const float* acc, int row_elems, float* out_row, int u, int n_lanes) {
     if ((row_elems & 3) == 0 && (reinterpret_cast<uintptr_t>(out_row) & 15) == 0) {
         const float4* s4 = reinterpret_cast<const float4*>(acc);
         float4* d4 = reinterpret_cast<float4*>(out_row);
-        for (int e = lane; e < row_elems / 4; e += 32) d4[e] = s4[e];
+        for (int e = u; e < row_elems / 4; e += n_lanes) d4[e] = s4[e];
     } else {
-        for (int e = lane; e < row_elems; e += 32) out_row[e] = acc[e];
+        for (int e = u; e < row_elems; e += n_lanes) out_row[e] = acc[e];
     }
 }
 

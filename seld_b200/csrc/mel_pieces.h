@@ -1,7 +1,8 @@
 // Host-side construction of the "piece" form of a triangular mel bank (used by seld_plan_create and by the CPU
 // emulation in tests/emu).  Input: dense [n_bins][n_mels] float32 table with at most two non-zeros per row, in adjacent
-// filters.  Lane l of a warp owns bins [l*bpt, (l+1)*bpt); a piece is a maximal run of one lane's bins feeding the same
-// filter pair (seg, seg + 1).  See Tables in extract_core.cuh for how the kernels consume these arrays.
+// filters.  Lane u of a frame team (kTeamLanes = 64 threads: the two warps that share one STFT frame) owns bins
+// [u*bpt, (u+1)*bpt); a piece is a maximal run of one lane's bins feeding the same filter pair (seg, seg + 1).  See
+// Tables in extract_core.cuh for how the kernels consume these arrays.
 #pragma once
 
 #include <string>
@@ -9,11 +10,13 @@
 
 namespace seld {
 
+constexpr int kTeamLanes = 64;
+
 struct MelPieces {
     int bpt = 0;                                  // bins per lane
-    std::vector<float> w01;                       // [32*bpt][2]  0.25 * (w into seg, w into seg + 1)
-    std::vector<unsigned long long> endmask;      // [32]
-    std::vector<int> piece0;                      // [32]
+    std::vector<float> w01;                       // [64*bpt][2]  0.25 * (w into seg, w into seg + 1)
+    std::vector<unsigned long long> endmask;      // [64]
+    std::vector<int> piece0;                      // [64]
     std::vector<int> pb;                          // [n_mels + 2]
     int n_pieces = 0;
     int max_pieces_per_seg = 0;
@@ -21,12 +24,13 @@ struct MelPieces {
 
 // returns "" on success, else an error message
 inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, MelPieces& out) {
-    const int bpt = (n_bins + 31) / 32;
+    constexpr int TL = kTeamLanes;
+    const int bpt = (n_bins + TL - 1) / TL;
     if (bpt > 64) return "too many bins per lane";
     out.bpt = bpt;
-    out.w01.assign(size_t(32) * bpt * 2, 0.f);
-    out.endmask.assign(32, 0ull);
-    out.piece0.assign(32, 0);
+    out.w01.assign(size_t(TL) * bpt * 2, 0.f);
+    out.endmask.assign(TL, 0ull);
+    out.piece0.assign(TL, 0);
     out.pb.assign(n_mels + 2, 0);
     std::vector<int> seg(n_bins, -1);
     for (int k = 0; k < n_bins; ++k) {
@@ -41,7 +45,7 @@ inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, Mel
     }
     std::vector<int> piece_seg;
     int prev_seg = -1;
-    for (int l = 0; l < 32; ++l) {
+    for (int l = 0; l < TL; ++l) {
         out.piece0[l] = int(piece_seg.size());
         int cur = -2, last_i = -1;
         for (int i = 0; i < bpt; ++i) {

@@ -19,14 +19,14 @@ struct seld_plan {
     float* window;   // [n_fft]
     float* twiddle;  // [n_fft][2]  exp(-2 pi i j / n_fft)
     float* tw_t;     // [n_fft/32][32][2]  tw_t[k2][lane] = exp(-2 pi i lane*k2 / n_fft)
-    float* w01;      // [32 * bins_per_lane][2]  piece form of the mel bank (mel_pieces.h)
-    unsigned long long* endmask;  // [32]
-    int* piece0;     // [32]
+    float* w01;      // [64 * bins_per_lane][2]  piece form of the mel bank (mel_pieces.h)
+    unsigned long long* endmask;  // [64]
+    int* piece0;     // [64]
     int* pb;         // [n_mels + 2]
     void* gcc_bt;    // MIC, n_fft 1024, 64 lags: fp16 [64][1024] basis of the tensor-core lag projection (else null)
     int n_pieces;
     int max_pieces_per_seg;
-    int e_bytes;     // per-warp exchange / piece buffer bytes
+    int e_bytes;     // per-team piece / GCC exchange buffer bytes
     // extract launch geometry
     int warps_per_cta;
     int extract_smem_bytes;

@@ -1,4 +1,4 @@
-// CPU emulation of one warp of the fused extractor: runs the per-lane phases of
+// CPU emulation of one frame team (two warps) of the fused extractor: runs the per-lane phases of
 // seld_b200/csrc/extract_core.cuh lane by lane (a phase boundary is a __syncwarp() on the device).
 // TEST INFRASTRUCTURE: lets the CPU suite check the kernel's index math, tables and FFT against the
 // oracle without a GPU.  Built by tests/test_emu_cpu.py with g++ -std=c++17.
@@ -13,7 +13,7 @@
 using namespace seld;
 
 template <int R, int MODE, int LAYOUT>
-static void run(const float* wav, int n_clips, long long L, int hop, int n_mels, const Tables& tb, bool gather3,
+static void run(const float* wav, int n_clips, long long L, int hop, int n_mels, const Tables& tb, bool fast_gather,
                 int T_out, float* out, float* clip_max) {
     using G = Geo<R>;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
@@ -21,8 +21,14 @@ static void run(const float* wav, int n_clips, long long L, int hop, int n_mels,
     float wreg[32][R];
     for (int l = 0; l < 32; ++l) for (int n2 = 0; n2 < R; ++n2) wreg[l][n2] = tb.window[l + 32 * n2];
     const int T_raw = 1 + int(L / hop);
-    std::vector<float2> E(G::E_ELEMS + 4096), S0(G::N), S1(G::N);
+    // team buffers as on the device: one exchange buffer per warp (the spectrum overwrites it in place), piece buffer X
+    std::vector<float2> EA(G::E_ELEMS), EB(G::E_ELEMS), X(G::E_ELEMS + 4096);
+    std::vector<float2> cols(size_t(32) * G::COLS * 32);
     std::vector<float> acc(size_t(n_mels) * C, 0.f);
+    auto stage2_inplace = [&](std::vector<float2>& buf) {
+        for (int l = 0; l < 32; ++l) stage2_load_fft<R>(buf.data(), cols.data() + size_t(l) * G::COLS * 32, l);
+        for (int l = 0; l < 32; ++l) stage2_store<R>(cols.data() + size_t(l) * G::COLS * 32, buf.data(), l);
+    };
     for (int clip = 0; clip < n_clips; ++clip) {
         ClipSrc src;
         src.base = wav + size_t(clip) * 4 * L;
@@ -35,27 +41,23 @@ static void run(const float* wav, int n_clips, long long L, int hop, int n_mels,
             float* row = (t < T_out) ? out + (size_t(clip) * T_out + t) * n_mels * C : nullptr;
             if (t >= T_raw) { memset(row, 0, sizeof(float) * n_mels * C); continue; }
             const long long start = (long long)t * hop - G::N / 2;
-            for (int l = 0; l < 32; ++l) stage1_forward<R, LAYOUT>(src, 0, 1, start, wreg[l], tb, E.data(), l);
-            for (int l = 0; l < 32; ++l) stage2_forward<R>(E.data(), S0.data(), l);
-            for (int l = 0; l < 32; ++l) stage1_forward<R, LAYOUT>(src, 2, 3, start, wreg[l], tb, E.data(), l);
-            for (int l = 0; l < 32; ++l) stage2_forward<R>(E.data(), S1.data(), l);
-            for (int l = 0; l < 32; ++l) bin_phase<R, MODE>(S0.data(), S1.data(), tb, E.data(), 1e-8f, l);
-            if (gather3) {
-                std::vector<float2> xchg(32 * 8);
-                for (int l = 0; l < 32; ++l) gather_pairs_publish<MODE>(E.data(), tb, n_mels, l, xchg.data());
-                for (int l = 0; l < 32; ++l) cmax = fmaxf(cmax, gather_pairs<MODE>(E.data(), tb, acc.data(), n_mels, l, xchg.data()));
-            } else {
-                for (int l = 0; l < 32; ++l) cmax = fmaxf(cmax, gather_phase<MODE, 0>(E.data(), tb, acc.data(), n_mels, l));
-            }
+            for (int l = 0; l < 32; ++l) stage1_forward<R, LAYOUT>(src, 0, 1, start, wreg[l], tb, EA.data(), l);
+            stage2_inplace(EA);
+            for (int l = 0; l < 32; ++l) stage1_forward<R, LAYOUT>(src, 2, 3, start, wreg[l], tb, EB.data(), l);
+            stage2_inplace(EB);
+            for (int u = 0; u < G::TL; ++u) bin_phase<R, MODE>(EA.data(), EB.data(), tb, X.data(), 1e-8f, u);
+            for (int u = 0; u < G::TL; ++u)
+                cmax = fmaxf(cmax, fast_gather ? gather_lanes<MODE>(X.data(), tb, acc.data(), n_mels, u)
+                                               : gather_phase<MODE, 0>(X.data(), tb, acc.data(), n_mels, u));
             if (MODE == MODE_MIC) {
-                for (int l = 0; l < 32; ++l) gcc_stage1<R, 0>(S0.data(), S1.data(), E.data(), l);
-                for (int l = 0; l < 32; ++l) gcc_stage2<R, 0>(E.data(), tb, acc.data(), n_mels, l);
-                for (int l = 0; l < 32; ++l) gcc_stage1<R, 1>(S0.data(), S1.data(), E.data(), l);
-                for (int l = 0; l < 32; ++l) gcc_stage2<R, 1>(E.data(), tb, acc.data(), n_mels, l);
-                for (int l = 0; l < 32; ++l) gcc_stage1<R, 2>(S0.data(), S1.data(), E.data(), l);
-                for (int l = 0; l < 32; ++l) gcc_stage2<R, 2>(E.data(), tb, acc.data(), n_mels, l);
+                for (int l = 0; l < 32; ++l) gcc_stage1<R, 0>(EA.data(), EB.data(), X.data(), l);
+                for (int l = 0; l < 32; ++l) gcc_stage2<R, 0>(X.data(), tb, acc.data(), n_mels, l);
+                for (int l = 0; l < 32; ++l) gcc_stage1<R, 1>(EA.data(), EB.data(), X.data(), l);
+                for (int l = 0; l < 32; ++l) gcc_stage2<R, 1>(X.data(), tb, acc.data(), n_mels, l);
+                for (int l = 0; l < 32; ++l) gcc_stage1<R, 2>(EA.data(), EB.data(), X.data(), l);
+                for (int l = 0; l < 32; ++l) gcc_stage2<R, 2>(X.data(), tb, acc.data(), n_mels, l);
             }
-            if (row) for (int l = 0; l < 32; ++l) store_row(acc.data(), n_mels * C, row, l);
+            if (row) for (int u = 0; u < G::TL; ++u) store_row(acc.data(), n_mels * C, row, u, G::TL);
         }
         clip_max[clip] = cmax;
     }
@@ -74,7 +76,7 @@ extern "C" int emu_extract(const float* wav, int layout, int n_clips, long long 
     static const float2 zero_rec[8] = {};
     Tables tb{window, tw_t.data(), lin, reinterpret_cast<const float2*>(mp.w01.data()), mp.endmask.data(), mp.piece0.data(),
               mp.pb.data(), zero_rec};
-#define GO3(RR, MM, LL) run<RR, MM, LL>(wav, n_clips, L, hop, n_mels, tb, mp.max_pieces_per_seg <= 3 && n_mels <= 64, T_out, out, clip_max)
+#define GO3(RR, MM, LL) run<RR, MM, LL>(wav, n_clips, L, hop, n_mels, tb, mp.max_pieces_per_seg <= GATHER_MAXP && n_mels <= 64, T_out, out, clip_max)
 #define GO(RR)                                                                   \
     if (n_fft == 32 * RR) {                                                      \
         if (mode == MODE_FOA) { if (layout == 0) GO3(RR, MODE_FOA, 0); else GO3(RR, MODE_FOA, 1); } \
