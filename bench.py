@@ -311,7 +311,7 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
                 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                 'data': 'synthetic', 'config': workload_config(args, n), 'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
-                'gpu_launches': 6 * args.steps, 'clocks': clocks}
+                'gpu_launches': (7 if mode == 'mic' else 6) * args.steps, 'clocks': clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,177 @@
+"""Windowing / batching glue of the reference's training input pipeline, on resident device tensors.
+
+Reference surface (data_loader.py):
+  data_loader(dataset, preprocessing, sample_transforms, batch_transforms, deterministic, loop_time, batch_size)  :13-56
+  seldnet_data_to_dataloader(features, labels, train, label_window_size, drop_remainder, shuffle_size,
+                             batch_size, loop_time, **kwargs)                                                    :132-168
+and the sliding-window evaluation framing of trainv2.py:158-192 (`ensemble_outputs`).
+
+The reference builds a tf.data graph over host numpy arrays; here the normalised features stay in HBM as one
+[sum T, F, C] tensor, a batch of consecutive windows is a zero-copy view of it, the sample transforms run as ONE fused
+masking launch per batch (`transforms.sample_masks`) and the batch transforms as one remap launch
+(`transforms.foa_intensity_vec_aug` ...).  Shapes, ordering (repeat -> batch -> batch-level shuffle) and the
+drop-remainder rule follow the reference; random streams are this package's own (seeded, reproducible).
+"""
+import numpy as np
+import torch
+
+__all__ = ['data_loader', 'seldnet_data_to_dataloader', 'frame_windows', 'overlap_and_add_mean', 'ensemble_outputs']
+
+
+def _as_tensor(a, device):
+    t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
+    return t.to(device) if device is not None else t
+
+
+def _apply(ops, x, y, per_sample):
+    """Apply a list of (x, y) -> (x, y) callables.  per_sample: the reference maps these over single samples; ops
+    carrying ``batched = True`` (transforms.sample_masks) take the whole batch in one launch instead."""
+    if ops is None:
+        return x, y
+    if not isinstance(ops, (list, tuple)):
+        ops = [ops]
+    for op in ops:
+        if not per_sample or getattr(op, 'batched', False):
+            x, y = op(x, y)
+        else:
+            outs = [op(x[i], y[i]) for i in range(x.shape[0])]
+            x = torch.stack([torch.as_tensor(o[0]) for o in outs])
+            y = torch.stack([torch.as_tensor(o[1]) for o in outs])
+    return x, y
+
+
+class _BatchIterable:
+    """repeat(loop_time) -> [sample transforms] -> batch(batch_size, drop_remainder=False) -> [batch transforms]
+    (reference data_loader.py:49-54), then an optional tf.data-style buffer shuffle of the BATCHES (:161-164)."""
+
+    def __init__(self, xs, ys, n_samples, batch_size, loop_time, sample_transforms, batch_transforms, shuffle_size, seed):
+        self.xs, self.ys, self.n = xs, ys, int(n_samples)
+        self.batch_size = int(batch_size)
+        self.loop_time = 1 if loop_time is None else int(loop_time)
+        self.sample_transforms, self.batch_transforms = sample_transforms, batch_transforms
+        self.shuffle_size = shuffle_size
+        self.rng = np.random.default_rng(seed)
+
+    def __len__(self):
+        return -(-self.n * self.loop_time // self.batch_size)
+
+    def batch_order(self):
+        """Batch indices in the order they are yielded (buffer shuffle: fill `shuffle_size` slots, emit a random slot,
+        refill it with the next batch -- tf.data.Dataset.shuffle semantics)."""
+        n_batches = len(self)
+        if not self.shuffle_size or self.shuffle_size <= 1:
+            return list(range(n_batches))
+        buf, out, nxt = [], [], 0
+        while nxt < n_batches and len(buf) < self.shuffle_size:
+            buf.append(nxt)
+            nxt += 1
+        while buf:
+            i = int(self.rng.integers(len(buf)))
+            out.append(buf[i])
+            if nxt < n_batches:
+                buf[i] = nxt
+                nxt += 1
+            else:
+                buf.pop(i)
+        return out
+
+    def _slice(self, lo, hi):
+        """Samples [lo, hi) of the repeated stream (contiguous views where the range does not wrap)."""
+        lo_m, hi_m = lo % self.n, (hi - 1) % self.n + 1
+        if lo // self.n == (hi - 1) // self.n:
+            return self.xs[lo_m:hi_m], self.ys[lo_m:hi_m]
+        return (torch.cat([self.xs[lo_m:], self.xs[:hi_m]]), torch.cat([self.ys[lo_m:], self.ys[:hi_m]]))
+
+    def __iter__(self):
+        total = self.n * self.loop_time
+        for b in self.batch_order():
+            lo, hi = b * self.batch_size, min((b + 1) * self.batch_size, total)
+            x, y = self._slice(lo, hi)
+            x, y = _apply(self.sample_transforms, x, y, per_sample=True)
+            x, y = _apply(self.batch_transforms, x, y, per_sample=False)
+            yield x, y
+
+
+def data_loader(dataset, preprocessing=None, sample_transforms=None, batch_transforms=None, deterministic=False,
+                loop_time=None, batch_size=32, shuffle_size=None, seed=0, device=None):
+    """reference data_loader.py:13-56.  ``dataset`` = (xs, ys) with a common leading sample axis (tensors or arrays).
+    ``preprocessing`` ops run once up front on the whole set (the reference caches their output); ``deterministic`` is
+    accepted for signature parity -- the order here is always deterministic given ``seed``."""
+    xs, ys = dataset
+    xs, ys = _as_tensor(xs, device), _as_tensor(ys, device)
+    xs, ys = _apply(preprocessing, xs, ys, per_sample=True)
+    return _BatchIterable(xs, ys, xs.shape[0], batch_size, loop_time, sample_transforms, batch_transforms, shuffle_size, seed)
+
+
+def seldnet_data_to_dataloader(features, labels, train=True, label_window_size=60, drop_remainder=True, shuffle_size=None,
+                               batch_size=32, loop_time=1, device=None, seed=0, **kwargs):
+    """reference data_loader.py:132-168.  features: list of [T_i, F, C] (or one [n, T, F, C] tensor), labels: list of
+    [T_i / resolution, 4 * n_classes] -> batches x [B, label_window_size * resolution, F, C], y [B, label_window_size,
+    4 * n_classes].  Windows are cut from the time-concatenated stream, non-overlapping, remainder dropped; evaluation
+    (train=False) yields one clip per batch, unshuffled, a single pass."""
+    if isinstance(features, (list, tuple)):
+        total_length = labels[0].shape[0]
+        feats = torch.cat([_as_tensor(f, device) for f in features], dim=0)
+        labs = torch.cat([_as_tensor(l, device) for l in labels], dim=0)
+    else:
+        feats, labs = _as_tensor(features, device), _as_tensor(labels, device)
+        total_length = labs.shape[1] if labs.dim() == 3 else labs.shape[0]
+        if feats.dim() == 4:
+            feats = feats.reshape(-1, *feats.shape[2:])
+        if labs.dim() == 3:
+            labs = labs.reshape(-1, labs.shape[-1])
+    if feats.shape[0] % labs.shape[0]:
+        raise ValueError('feature frames must be a multiple of label frames')
+    resolution = feats.shape[0] // labs.shape[0]
+    lws = int(label_window_size)
+    n_samples = labs.shape[0] // lws
+    if not drop_remainder and labs.shape[0] % lws:
+        raise ValueError('a ragged last window cannot be batched (the reference fails there too): use drop_remainder=True')
+    xs = feats[:n_samples * lws * resolution].reshape(n_samples, lws * resolution, *feats.shape[1:])     # views, no copy
+    ys = labs[:n_samples * lws].reshape(n_samples, lws, labs.shape[-1])
+    if not train:
+        batch_size = total_length // lws
+    shuffle = None
+    if train:
+        shuffle = n_samples // batch_size if shuffle_size is None else shuffle_size
+    return _BatchIterable(xs, ys, n_samples, batch_size, loop_time if train else 1, kwargs.get('sample_transforms'),
+                          kwargs.get('batch_transforms'), shuffle, seed)
+
+
+# --------------------------------------------------------------------------- sliding-window evaluation (trainv2.py:158-192)
+def frame_windows(x, win_size=300, step_size=5):
+    """tf.signal.frame(x, win_size, step_size, axis=0) as a zero-copy strided view [n_win, win_size, ...]."""
+    if not x.is_contiguous():
+        x = x.contiguous()
+    n_win = (x.shape[0] - win_size) // step_size + 1
+    if n_win <= 0:
+        return x.new_empty((0, win_size) + tuple(x.shape[1:]))
+    inner = x.stride(0)
+    return x.as_strided((n_win, win_size) + tuple(x.shape[1:]), (step_size * inner, inner) + tuple(x.stride()[1:]))
+
+
+def overlap_and_add_mean(frames):
+    """frames [n_win, L, K] of window outputs hopping by ONE output step -> [n_win + L - 1, K]: overlap-add divided by
+    the overlap count (tf.signal.overlap_and_add(..., 1) / total_counts, trainv2.py:173-179)."""
+    n_win, length, k = frames.shape
+    out = frames.new_zeros(n_win + length - 1, k)
+    cnt = frames.new_zeros(n_win + length - 1, 1)
+    idx = (torch.arange(n_win, device=frames.device)[:, None] + torch.arange(length, device=frames.device)[None, :]).reshape(-1)
+    out.index_add_(0, idx, frames.reshape(-1, k))
+    cnt.index_add_(0, idx, frames.new_ones(idx.numel(), 1))
+    return out / cnt
+
+
+def ensemble_outputs(model, xs, win_size=300, step_size=5, batch_size=256):
+    """trainv2.py:158-192: run ``model`` (a callable: windows [b, win, F, C] -> (sed [b, win/5, n], doa [b, win/5, m])) over
+    every ``step_size``-hop window of each clip and average the overlapping per-label-frame outputs."""
+    outs = []
+    for x in xs:
+        windows = frame_windows(_as_tensor(x, None), win_size, step_size)
+        sed, doa = [], []
+        for i in range(0, windows.shape[0], batch_size):
+            s, d = model(windows[i:i + batch_size])
+            sed.append(s)
+            doa.append(d)
+        outs.append((overlap_and_add_mean(torch.cat(sed)), overlap_and_add_mean(torch.cat(doa))))
+    return outs

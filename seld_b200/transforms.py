@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 
-__all__ = ['mask', 'simple_mask', 'mask_batch_', 'set_seed', 'set_counter_seed', 'foa_intensity_vec_aug', 'acs_aug',
+__all__ = ['mask', 'simple_mask', 'mask_batch_', 'sample_masks', 'set_seed', 'set_counter_seed', 'foa_intensity_vec_aug', 'acs_aug',
            'mic_gcc_perm', 'channel_list', 'split_total_labels_to_sed_doa']
 
 _MAXINT32 = 2 ** 31 - 1
@@ -171,6 +171,18 @@ def mask_batch_(x, time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, 
         sample_offset = 0
     return _launch(x, b, t, 1, f, c, int(period), tm, int(tn), fm, int(fn), int(seed) & (2 ** 64 - 1), int(sample_offset),
                    _lib.RNG_PHILOX_COUNTER, None, return_draws)
+
+
+def sample_masks(time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None):
+    """The reference's per-sample masking lambdas (train.py:157-160: ``mask(x, axis=-3, max_mask_size=24, n_mask=1)`` then
+    ``mask(x, axis=-2, max_mask_size=16)``) as ONE batched transform for ``data_loader.seldnet_data_to_dataloader``:
+    ``(x [B, T, F, C], y) -> (masked copy of x, y)``, independent draws per sample, one fused launch per batch."""
+    def op(x, y):
+        out = x.clone(memory_format=torch.contiguous_format)
+        mask_batch_(out, time_mask, freq_mask, period=period, seed=seed)
+        return out, y
+    op.batched = True
+    return op
 
 
 # --------------------------------------------------------------------------- batch-level spatial augmentations (f1)
