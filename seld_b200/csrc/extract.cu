@@ -57,11 +57,13 @@ struct ExtractArgs {
     const float2* tw_lin;
     const float2* w01;
     const unsigned long long* endmask;
-    const int* piece0;
+    const int* slot0;
+    const int* slot1;
     const int* pb;
     int hop, n_mels;
     int e_bytes;              // per-team piece / GCC exchange buffer size
-    int gather_unrolled;      // every mel segment has <= GATHER_MAXP pieces and n_mels <= 64: gather_lanes
+    int seg_major;            // piece records in the segment-major layout: gather_lanes (else the compact layout + gather_phase)
+    int x_zero_f2;            // float2 elements of the piece buffer that must read as zero where no piece is stored
     int gcc_tc;               // MIC: write fp16 pair phasors to gcc_rows; the tensor-core GEMM does the lag projection
     int t_g;                  // frames per clip that have a stored row (min(t_raw, t_out))
     float* gcc_rows;          // tile-blocked fp16 pair phasors, A operand of gcc_gemm (21 frames = 126 rows per tile)
@@ -69,7 +71,6 @@ struct ExtractArgs {
     int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
     int origin;               // frame t starts at sample t*hop - n_fft/2 + origin (0: centred STFT; n_fft/2: uncentred chunks)
     int fpw;                  // consecutive frames per team per super-chunk
-    int assign_blocked;       // 0: super-chunk sc -> CTA sc mod grid; 1: each CTA walks one contiguous range
     int fsc;                  // frames per super-chunk (teams * fpw)
     long long n_super;        // super-chunks of fsc frames
 };
@@ -86,7 +87,7 @@ __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 template <int R, int MODE>
 __host__ __device__ constexpr int table_bytes(int n_mels) {
     using G = Geo<R>;
-    return align16(G::N * 8) + align16(G::TL * G::BPT * 8) + align16(G::TL * 8) + align16(G::TL * 4) + align16((n_mels + 2) * 4) + 64 +
+    return align16(G::N * 8) + align16(G::TL * G::BPT * 8) + align16(G::TL * 8) + 2 * align16(G::TL * 4) + align16((n_mels + 2) * 4) + 64 +
            align16(G::N * 4) + (MODE == MODE_MIC ? align16(G::N * 8) : 0);
 }
 // One frame team (two warps): an exchange buffer per warp (its spectrum overwrites it in place), the piece / GCC exchange
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     float2* s_tw_t = reinterpret_cast<float2*>(p);  p += align16(G::N * 8);
     float2* s_w01 = reinterpret_cast<float2*>(p);  p += align16(TL * G::BPT * 8);
     unsigned long long* s_endmask = reinterpret_cast<unsigned long long*>(p);  p += align16(TL * 8);
-    int* s_piece0 = reinterpret_cast<int*>(p);  p += align16(TL * 4);
+    int* s_slot0 = reinterpret_cast<int*>(p);  p += align16(TL * 4);
+    int* s_slot1 = reinterpret_cast<int*>(p);  p += align16(TL * 4);
     int* s_pb = reinterpret_cast<int*>(p);  p += align16((a.n_mels + 2) * 4);
     float2* s_zero = reinterpret_cast<float2*>(p);  p += 64;
     float* s_win = reinterpret_cast<float*>(p);  p += align16(G::N * 4);
@@ -138,7 +140,11 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     }
     for (int i = threadIdx.x; i < TL * G::BPT; i += blockDim.x) s_w01[i] = a.w01[i];
     for (int i = threadIdx.x; i < a.n_mels + 2; i += blockDim.x) s_pb[i] = a.pb[i];
-    if (threadIdx.x < TL) { s_endmask[threadIdx.x] = a.endmask[threadIdx.x]; s_piece0[threadIdx.x] = a.piece0[threadIdx.x]; }
+    if (threadIdx.x < TL) {
+        s_endmask[threadIdx.x] = a.endmask[threadIdx.x];
+        s_slot0[threadIdx.x] = a.slot0[threadIdx.x];
+        s_slot1[threadIdx.x] = a.slot1[threadIdx.x];
+    }
     if (threadIdx.x < 8) s_zero[threadIdx.x] = make_float2(0.f, 0.f);
     // ---- per-team regions
     unsigned char* tp = p + size_t(team) * team_bytes<R, MODE>(a.n_mels, a.e_bytes);
@@ -148,12 +154,13 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     float* acc = reinterpret_cast<float*>(tp);
     float2* E = h ? S1 : S0;
     const int row_elems = a.n_mels * C;
+    for (int i = u; i < a.x_zero_f2; i += TL) X[i] = make_float2(0.f, 0.f);    // segment-major slots without a piece stay zero
     __syncthreads();
     // window taps of this lane: s_win[lane + 32 n2].  The interior kernel reads them from shared memory per frame (at 168
     // registers per thread a register copy would be spilled to local memory anyway); the edge kernel keeps a copy.
     const float* wlane = s_win + lane;
 
-    const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_piece0, s_pb, s_zero};
+    const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_slot0, s_slot1, s_pb, s_zero};
     const long long total_frames = (long long)a.n_clips * a.frames_per_clip;
 
     float run_max = -INFINITY;
@@ -165,8 +172,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
         team_bar(bar_id);                                            // both spectra are in place
         bin_phase<R, MODE, tc>(S0, S1, tb, X, 1e-8f, u);
         team_bar(bar_id);
-        float mx = a.gather_unrolled ? gather_lanes<MODE>(X, tb, acc, a.n_mels, u)
-                                     : gather_phase<MODE, 0>(X, tb, acc, a.n_mels, u);
+        float mx = a.seg_major ? gather_lanes<MODE>(X, acc, a.n_mels, u) : gather_phase<MODE>(X, tb, acc, a.n_mels, u);
         if constexpr (MODE == MODE_MIC && !tc) {
             team_bar(bar_id);                                        // pieces consumed: X is the GCC exchange buffer now
             if (h == 0) {
@@ -181,6 +187,8 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
                 gcc_stage1<R, 2>(S0, S1, X, lane);
                 __syncwarp();
                 gcc_stage2<R, 2>(X, tb, acc, a.n_mels, lane);
+                __syncwarp();
+                for (int i = lane; i < a.x_zero_f2; i += 32) X[i] = make_float2(0.f, 0.f);   // X goes back to being the piece buffer
             }
         }
         team_bar(bar_id);                                            // the row is complete
@@ -244,10 +252,9 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
         // Interior frames, software-pipelined: the raw samples of the team's NEXT frame (this warp's channel pair) are
         // requested before the current frame's FFT starts, so HBM/L2 latency hides behind the arithmetic (requesting them
         // later -- after the bin phase -- measured 6 % slower).
-        const long long sc_step = a.assign_blocked ? 1 : gridDim.x;
-        const long long per_cta = (a.n_super + gridDim.x - 1) / gridDim.x;
-        long long sc = a.assign_blocked ? blockIdx.x * per_cta : blockIdx.x;
-        const long long sc_end = a.assign_blocked ? (sc + per_cta < a.n_super ? sc + per_cta : a.n_super) : a.n_super;
+        const long long sc_step = gridDim.x;              // super-chunk sc -> CTA sc mod grid
+        long long sc = blockIdx.x;
+        const long long sc_end = a.n_super;
         int fi = 0;
         auto frame_index = [&](long long s, int i) -> long long {       // -1 past the end
             if (s >= sc_end || team * a.fpw + i >= a.fsc) return -1;
@@ -304,7 +311,6 @@ static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream)
     a.frames_per_clip = EDGE ? a.t_lo + (a.t_tot - a.t_hi) : a.t_hi - a.t_lo;
     if (a.frames_per_clip <= 0) return SELD_OK;
     a.fpw = frames_per_warp();
-    a.assign_blocked = 0;
     a.fsc = (plan->warps_per_cta / 2) * a.fpw;
     const long long per_super = a.fsc;
     a.n_super = ((long long)a.n_clips * a.frames_per_clip + per_super - 1) / per_super;
@@ -362,7 +368,7 @@ static void plan_geometry_mode(seld_plan* plan) {
     using G = Geo<R>;
     const int pstride = PieceGeo<MODE>::PSTRIDE * 8;
     int e_bytes = align16(G::E_ELEMS * 8);
-    if (plan->n_pieces * pstride > e_bytes) e_bytes = align16(plan->n_pieces * pstride);
+    if (plan->n_slots * pstride > e_bytes) e_bytes = align16(plan->n_slots * pstride);
     plan->e_bytes = e_bytes;
     const int tb = table_bytes<R, MODE>(plan->n_mels);
     const int wb = team_bytes<R, MODE>(plan->n_mels, e_bytes);
@@ -456,6 +462,8 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
     }
     plan->n_pieces = mp.n_pieces;
     plan->max_pieces_per_seg = mp.max_pieces_per_seg;
+    plan->n_slots = mp.n_slots;
+    plan->seg_major = mp.seg_major ? 1 : 0;
     std::vector<float> tw(2 * (size_t)n_fft);
     for (int j = 0; j < n_fft; ++j) {
         const double ang = -2.0 * 3.14159265358979323846264338327950288 * double(j) / double(n_fft);
@@ -480,7 +488,8 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
     up((void**)&plan->tw_t, twt.data(), sizeof(float) * 2 * n_fft);
     up((void**)&plan->w01, mp.w01.data(), sizeof(float) * mp.w01.size());
     up((void**)&plan->endmask, mp.endmask.data(), sizeof(unsigned long long) * mp.endmask.size());
-    up((void**)&plan->piece0, mp.piece0.data(), sizeof(int) * mp.piece0.size());
+    up((void**)&plan->slot0, mp.slot0.data(), sizeof(int) * mp.slot0.size());
+    up((void**)&plan->slot1, mp.slot1.data(), sizeof(int) * mp.slot1.size());
     up((void**)&plan->pb, mp.pb.data(), sizeof(int) * mp.pb.size());
     if (e != cudaSuccess) {
         seld_plan_destroy(plan);
@@ -536,7 +545,8 @@ int seld_plan_destroy(seld_plan_t plan) {
     cudaFree(plan->tw_t);
     cudaFree(plan->w01);
     cudaFree(plan->endmask);
-    cudaFree(plan->piece0);
+    cudaFree(plan->slot0);
+    cudaFree(plan->slot1);
     cudaFree(plan->pb);
     cudaFree(plan->gcc_bt);
     delete plan;
@@ -591,7 +601,8 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
     a.tw_lin = reinterpret_cast<const float2*>(plan->twiddle);
     a.w01 = reinterpret_cast<const float2*>(plan->w01);
     a.endmask = plan->endmask;
-    a.piece0 = plan->piece0;
+    a.slot0 = plan->slot0;
+    a.slot1 = plan->slot1;
     a.pb = plan->pb;
     a.e_bytes = plan->e_bytes;
     a.t_g = a.t_raw < t_out ? a.t_raw : t_out;
@@ -605,7 +616,8 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
             a.gcc_logmel = a.gcc_rows + ((frames + 20) / 21) * 128 * 512;
         }
     }
-    a.gather_unrolled = plan->max_pieces_per_seg <= GATHER_MAXP && plan->n_mels <= 64;
+    a.seg_major = plan->seg_major;
+    a.x_zero_f2 = plan->seg_major ? plan->n_slots * (plan->mode == SELD_MODE_FOA ? PieceGeo<MODE_FOA>::PSTRIDE : PieceGeo<MODE_MIC>::PSTRIDE) : 0;
     // frames [t_lo, t_hi) need no reflection: t*hop - n_fft/2 >= 0 and t*hop + n_fft/2 <= n_samples
     {
         const long long half = plan->n_fft / 2;

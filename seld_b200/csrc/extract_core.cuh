@@ -26,6 +26,7 @@
 #pragma once
 
 #include "seld_common.cuh"
+#include "mel_pieces.h"
 #if defined(__CUDACC__)
 #include <cuda_fp16.h>
 #endif
@@ -43,8 +44,9 @@ struct Tables {             // CTA-shared constant tables (shared memory on the 
     // a maximal run of one lane's bins that feed the same pair of adjacent filters (seg, seg+1)
     const float2* w01;          // [TL*BPT] 0.25 * (weight into filter seg, weight into filter seg+1); 0 past bin F-1
     const unsigned long long* endmask;  // [TL] bit i set: bin u*BPT + i is the last bin of a piece
-    const int* piece0;          // [TL]     index of lane u's first piece
-    const int* pb;              // [n_mels + 2] pieces with seg == m are [pb[m+1], pb[m+2])
+    const int* slot0;           // [TL]     record slot of lane u's first piece
+    const int* slot1;           // [TL]     slot of its second piece (later pieces follow at +1); layouts: mel_pieces.h
+    const int* pb;              // [n_mels + 2] compact layout: pieces with seg == m are [pb[m+1], pb[m+2])
     const float2* zero_rec;     // [8] zeros: a piece record that contributes nothing
 };
 
@@ -155,28 +157,8 @@ SELD_HD void pfft_dif(float2* v) {
 // wreg[n2] = window[lane + 32*n2] is held in registers by the caller for the whole kernel.
 // Interior frames (whole frame inside the clip, no reflection): one 64-bit load per tap when the two channels
 // of the pair are adjacent in memory (interleaved layout, ch_b == ch_a + 1, ch_a even), else two 32-bit loads.
-// streaming-load helpers (L1 no-allocate).  Measured on B200: planar 11.8 -> 12.15 ms, interleaved 12.9 -> 15.1 ms per 600
-// clips, because the second channel pair of an interleaved frame re-reads the sectors the first pair brought into L1;
-// the hot loads therefore use plain ld.global and these stay unused.
-SELD_HD float ld_stream(const float* p) {
-#if defined(__CUDA_ARCH__)
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-#else
-    return *p;
-#endif
-}
-SELD_HD float2 ld_stream2(const float2* p) {
-#if defined(__CUDA_ARCH__)
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-#else
-    return *p;
-#endif
-}
-
+// (Streaming L1::no_allocate loads were measured and rejected: planar 11.8 -> 12.15 ms, interleaved 12.9 -> 15.1 ms per
+// 600 clips -- neighbouring frames re-read the sectors the first one brought into L1.)
 template <int R, int LAYOUT>
 SELD_HD void stage1_load_raw(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, float2* raw, int lane) {
     if constexpr (LAYOUT == LAYOUT_INTERLEAVED_LC) {
@@ -191,17 +173,10 @@ SELD_HD void stage1_load_raw(const ClipSrc& src, int ch_a, int ch_b, long long f
     }
 }
 
-// ---- 16-bit PCM input (the payload of a WAV file, 4 interleaved channels = 8 bytes per sample).  One 64-bit load per
-// tap brings all four channels, i.e. BOTH packed FFT inputs of the frame.  int16 -> float without I2F: put the 16 bits
+// ---- 16-bit PCM input (the payload of a WAV file, 4 interleaved channels = 8 bytes per sample).  One 32-bit load per
+// tap brings the two channels of this warp's packed FFT input.  int16 -> float without I2F: put the 16 bits
 // (offset-binary) into the mantissa of 2^23 and subtract 2^23 + 2^15; the 1/32768 of torchaudio's decoder is folded
 // into the window taps (an exact power-of-two scaling), so the result equals window * (s / 32768) bit for bit.
-template <int R>
-SELD_HD void stage1_load_raw_pcm16(const short* base, long long frame_start, float2* raw, int lane) {
-    const float2* p = reinterpret_cast<const float2*>(base + (frame_start + lane) * 4);    // 8 bytes per sample
-#pragma unroll
-    for (int n2 = 0; n2 < R; ++n2) raw[n2] = p[32 * n2];
-}
-
 // One channel pair only (32-bit load per tap): the team's warp `pair` reads its half of every 8-byte sample.
 template <int R>
 SELD_HD void stage1_load_raw_pcm16_pair(const short* base, int pair, long long frame_start, float2* raw, int lane) {
@@ -458,7 +433,7 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
     constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
     const int kbeg = u * G::BPT;
     const unsigned long long endmask = tb.endmask[u];
-    int piece = tb.piece0[u];
+    int slot = tb.slot0[u], next = tb.slot1[u];
     float2 acc2[NV];
 #pragma unroll
     for (int c = 0; c < NV; ++c) acc2[c] = make_float2(0.f, 0.f);
@@ -520,8 +495,9 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
 #pragma unroll
         for (int c = 0; c < NV; ++c) acc2[c] = pfma(make_float2(val[c], val[c]), w, acc2[c]);
         const unsigned flag = static_cast<unsigned>(endmask >> i) & 1u;
-        piece_flush<NV>(acc2, P + piece * PSTRIDE, flag);
-        piece += int(flag);
+        piece_flush<NV>(acc2, P + slot * PSTRIDE, flag);
+        slot = flag ? next : slot;
+        next += int(flag);
     }
 }
 
@@ -536,7 +512,7 @@ SELD_HD float fast_db(float x) {            // 10 log10(x), x > 0
 // ---------------------------------------------------------------- gather: pieces -> mel rows
 // Team lane u owns filters m = u, u + TL, ...: mel[m][c] = sum_{pieces of seg m} P.x + sum_{pieces of seg m-1} P.y, in
 // piece order.  Log-mel channels get 10 log10(max(., 1e-10)) here; returns the lane's maximum dB.
-template <int MODE, int MAXP>
+template <int MODE>
 SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_mels, int u) {
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
@@ -547,33 +523,15 @@ SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_
         float sum[NV];
 #pragma unroll
         for (int c = 0; c < NV; ++c) sum[c] = 0.f;
-        if constexpr (MAXP > 0) {
-            // at most MAXP pieces per segment (checked when the plan is built): straight-line, independent loads
-#pragma unroll
-            for (int j = 0; j < MAXP; ++j) {
-                const bool on = p0 + j < p1;
-                const int p = on ? p0 + j : p0;
-#pragma unroll
-                for (int c = 0; c < NV; ++c) { const float t = P[p * PSTRIDE + c].y; sum[c] += on ? t : 0.f; }
-            }
-#pragma unroll
-            for (int j = 0; j < MAXP; ++j) {
-                const bool on = p1 + j < p2;
-                const int p = on ? p1 + j : p1;
-#pragma unroll
-                for (int c = 0; c < NV; ++c) { const float t = P[p * PSTRIDE + c].x; sum[c] += on ? t : 0.f; }
-            }
-        } else {
 #pragma unroll 1
-            for (int p = p0; p < p1; ++p) {                // falling slopes of the segment below
+        for (int p = p0; p < p1; ++p) {                // falling slopes of the segment below
 #pragma unroll
-                for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].y;
-            }
+            for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].y;
+        }
 #pragma unroll 1
-            for (int p = p1; p < p2; ++p) {                // rising slopes of this filter's own segment
+        for (int p = p1; p < p2; ++p) {                // rising slopes of this filter's own segment
 #pragma unroll
-                for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].x;
-            }
+            for (int c = 0; c < NV; ++c) sum[c] += P[p * PSTRIDE + c].x;
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -587,48 +545,50 @@ SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_
     return mx;
 }
 
-// Fast gather for n_mels <= TL and <= GATHER_MAXP pieces per segment: team lane u totals the pieces of segment u with
-// packed adds (missing pieces read an all-zero record); mel[u] = A[u].x + A[u-1].y takes one shuffle per channel from the
-// lane below -- lane 0 of the team's second warp re-totals segment u-1 itself (same additions in the same order, so the
-// CPU emulation, which always re-totals, is bit-identical).
-constexpr int GATHER_MAXP = 4;
-
+// Fast gather over the segment-major record layout (mel_pieces.h): team lane u totals slots u + 65 j, j < 4, with packed
+// adds -- consecutive lanes read consecutive records (no bank conflicts) and absent pieces are slots that were zeroed once
+// and never written.  mel[u] = A[u].x + A[u-1].y takes one shuffle per channel from the lane below; lane 0 of the team's
+// second warp re-totals segment 31 itself (same additions in the same order, so the CPU emulation, which always
+// re-totals, is bit-identical).
 template <int MODE>
-SELD_HD void seg_total(const float2* P, const Tables& tb, int seg, int n_mels, float2* A) {
+SELD_HD void seg_total(const float2* P, int seg, float2* A) {
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
-    const bool on = seg >= 0 && seg < n_mels;
-    const int ps = on ? tb.pb[seg + 1] : 0, pe = on ? tb.pb[seg + 2] : 0;
+    const float2* rec = P + seg * PSTRIDE;
 #pragma unroll
-    for (int c = 0; c < NV; ++c) A[c] = make_float2(0.f, 0.f);
+    for (int c = 0; c < NV; ++c) A[c] = rec[c];
 #pragma unroll
-    for (int j = 0; j < GATHER_MAXP; ++j) {
-        const float2* rec = (ps + j < pe) ? P + (ps + j) * PSTRIDE : tb.zero_rec;
+    for (int j = 1; j < kSegMajorRanks; ++j) {
 #pragma unroll
-        for (int c = 0; c < NV; ++c) A[c] = padd(A[c], rec[c]);
+        for (int c = 0; c < NV; ++c) A[c] = padd(A[c], rec[j * kSegMajorPitch * PSTRIDE + c]);
     }
 }
 
 template <int MODE>
-SELD_HD float gather_lanes(const float2* P, const Tables& tb, float* acc, int n_mels, int u) {
+SELD_HD float gather_lanes(const float2* P, float* acc, int n_mels, int u) {
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
     float2 A[NV];
-    seg_total<MODE>(P, tb, u, n_mels, A);
+    seg_total<MODE>(P, u, A);
     float below[NV];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
     for (int c = 0; c < NV; ++c) below[c] = __shfl_up_sync(0xffffffffu, A[c].y, 1);
-    if ((u & 31) == 0) {
+    if (u == 0) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) below[c] = 0.f;
+    }
+    if (u == 32) {                                         // only the team's second warp takes this path
         float2 B[NV];
-        seg_total<MODE>(P, tb, u - 1, n_mels, B);          // all zero for u == 0
+        seg_total<MODE>(P, 31, B);
 #pragma unroll
         for (int c = 0; c < NV; ++c) below[c] = B[c].y;
     }
 #else
-    {
+    for (int c = 0; c < NV; ++c) below[c] = 0.f;
+    if (u > 0) {
         float2 B[NV];
-        seg_total<MODE>(P, tb, u - 1, n_mels, B);
+        seg_total<MODE>(P, u - 1, B);
         for (int c = 0; c < NV; ++c) below[c] = B[c].y;
     }
 #endif

@@ -16,11 +16,21 @@ struct MelPieces {
     int bpt = 0;                                  // bins per lane
     std::vector<float> w01;                       // [64*bpt][2]  0.25 * (w into seg, w into seg + 1)
     std::vector<unsigned long long> endmask;      // [64]
-    std::vector<int> piece0;                      // [64]
-    std::vector<int> pb;                          // [n_mels + 2]
+    std::vector<int> slot0;                       // [64] record slot of the lane's first piece
+    std::vector<int> slot1;                       // [64] record slot of its second piece; later pieces follow at +1
+    std::vector<int> pb;                          // [n_mels + 2]  (compact layout only)
     int n_pieces = 0;
     int max_pieces_per_seg = 0;
+    // Record layout.  compact: slot = piece index (pieces sorted by segment; the gather walks pb[]).
+    // seg_major (n_mels <= 64, <= kSegMajorRanks pieces per segment, no empty segment inside a lane's run): the j-th
+    // piece of segment s sits at slot s + kSegMajorPitch * j, so gather lane u reads slots u + kSegMajorPitch * j --
+    // consecutive lanes hit consecutive records (bank-conflict free) and absent pieces are slots that stay zero.
+    bool seg_major = false;
+    int n_slots = 0;
 };
+
+constexpr int kSegMajorRanks = 4;
+constexpr int kSegMajorPitch = 65;      // odd, so the <= 4 pieces of one segment land in different bank groups
 
 // returns "" on success, else an error message
 inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, MelPieces& out) {
@@ -30,7 +40,8 @@ inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, Mel
     out.bpt = bpt;
     out.w01.assign(size_t(TL) * bpt * 2, 0.f);
     out.endmask.assign(TL, 0ull);
-    out.piece0.assign(TL, 0);
+    out.slot0.assign(TL, 0);
+    out.slot1.assign(TL, 0);
     out.pb.assign(n_mels + 2, 0);
     std::vector<int> seg(n_bins, -1);
     for (int k = 0; k < n_bins; ++k) {
@@ -44,9 +55,10 @@ inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, Mel
         if (count == 2) out.w01[2 * size_t(k) + 1] = 0.25f * fb[size_t(k) * n_mels + last];
     }
     std::vector<int> piece_seg;
+    std::vector<int> first_piece(TL + 1, 0);
     int prev_seg = -1;
     for (int l = 0; l < TL; ++l) {
-        out.piece0[l] = int(piece_seg.size());
+        first_piece[l] = int(piece_seg.size());
         int cur = -2, last_i = -1;
         for (int i = 0; i < bpt; ++i) {
             const int k = l * bpt + i;
@@ -65,6 +77,7 @@ inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, Mel
             piece_seg.push_back(cur);
         }
     }
+    first_piece[TL] = int(piece_seg.size());
     out.n_pieces = int(piece_seg.size());
     out.max_pieces_per_seg = 0;
     for (size_t i = 0, run = 0; i < piece_seg.size(); ++i) {
@@ -77,6 +90,24 @@ inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, Mel
         while (p < out.n_pieces && piece_seg[p] < j - 1) ++p;
         out.pb[j] = p;
     }
+    // record slots
+    out.seg_major = n_mels <= 64 && out.max_pieces_per_seg <= kSegMajorRanks;
+    for (int l = 0; l < TL && out.seg_major; ++l)
+        for (int p = first_piece[l] + 1; p < first_piece[l + 1]; ++p)
+            if (piece_seg[p] != piece_seg[p - 1] + 1) out.seg_major = false;          // an empty segment inside the run
+    for (int l = 0; l < TL; ++l) {
+        const int p = first_piece[l];
+        if (!out.seg_major || p >= first_piece[l + 1]) {
+            out.slot0[l] = out.seg_major ? 0 : p;             // (a lane without pieces never stores)
+            out.slot1[l] = out.slot0[l] + 1;
+            continue;
+        }
+        int rank = 0;
+        while (p - rank - 1 >= 0 && piece_seg[p - rank - 1] == piece_seg[p]) ++rank;
+        out.slot0[l] = piece_seg[p] + kSegMajorPitch * rank;
+        out.slot1[l] = piece_seg[p] + 1;
+    }
+    out.n_slots = out.seg_major ? 64 + kSegMajorPitch * (kSegMajorRanks - 1) : out.n_pieces;
     return "";
 }
 

@@ -21,10 +21,13 @@ struct seld_plan {
     float* tw_t;     // [n_fft/32][32][2]  tw_t[k2][lane] = exp(-2 pi i lane*k2 / n_fft)
     float* w01;      // [64 * bins_per_lane][2]  piece form of the mel bank (mel_pieces.h)
     unsigned long long* endmask;  // [64]
-    int* piece0;     // [64]
+    int* slot0;      // [64]  record slot of each team lane's first / second piece (mel_pieces.h)
+    int* slot1;      // [64]
     int* pb;         // [n_mels + 2]
     void* gcc_bt;    // MIC, n_fft 1024, 64 lags: fp16 [64][1024] basis of the tensor-core lag projection (else null)
     int n_pieces;
+    int n_slots;     // piece records per frame in the layout in use
+    int seg_major;   // segment-major record layout (fast gather) instead of the compact one
     int max_pieces_per_seg;
     int e_bytes;     // per-team piece / GCC exchange buffer bytes
     // extract launch geometry

@@ -47,8 +47,8 @@ static void run(const float* wav, int n_clips, long long L, int hop, int n_mels,
             stage2_inplace(EB);
             for (int u = 0; u < G::TL; ++u) bin_phase<R, MODE>(EA.data(), EB.data(), tb, X.data(), 1e-8f, u);
             for (int u = 0; u < G::TL; ++u)
-                cmax = fmaxf(cmax, fast_gather ? gather_lanes<MODE>(X.data(), tb, acc.data(), n_mels, u)
-                                               : gather_phase<MODE, 0>(X.data(), tb, acc.data(), n_mels, u));
+                cmax = fmaxf(cmax, fast_gather ? gather_lanes<MODE>(X.data(), acc.data(), n_mels, u)
+                                               : gather_phase<MODE>(X.data(), tb, acc.data(), n_mels, u));
             if (MODE == MODE_MIC) {
                 for (int l = 0; l < 32; ++l) gcc_stage1<R, 0>(EA.data(), EB.data(), X.data(), l);
                 for (int l = 0; l < 32; ++l) gcc_stage2<R, 0>(X.data(), tb, acc.data(), n_mels, l);
@@ -56,6 +56,7 @@ static void run(const float* wav, int n_clips, long long L, int hop, int n_mels,
                 for (int l = 0; l < 32; ++l) gcc_stage2<R, 1>(X.data(), tb, acc.data(), n_mels, l);
                 for (int l = 0; l < 32; ++l) gcc_stage1<R, 2>(EA.data(), EB.data(), X.data(), l);
                 for (int l = 0; l < 32; ++l) gcc_stage2<R, 2>(X.data(), tb, acc.data(), n_mels, l);
+                std::fill(X.begin(), X.end(), make_float2(0.f, 0.f));        // X goes back to being the piece buffer
             }
             if (row) for (int u = 0; u < G::TL; ++u) store_row(acc.data(), n_mels * C, row, u, G::TL);
         }
@@ -74,9 +75,9 @@ extern "C" int emu_extract(const float* wav, int layout, int n_clips, long long 
     MelPieces mp;
     if (!build_mel_pieces(mel_fb, n_fft / 2 + 1, n_mels, mp).empty()) return -2;
     static const float2 zero_rec[8] = {};
-    Tables tb{window, tw_t.data(), lin, reinterpret_cast<const float2*>(mp.w01.data()), mp.endmask.data(), mp.piece0.data(),
+    Tables tb{window, tw_t.data(), lin, reinterpret_cast<const float2*>(mp.w01.data()), mp.endmask.data(), mp.slot0.data(), mp.slot1.data(),
               mp.pb.data(), zero_rec};
-#define GO3(RR, MM, LL) run<RR, MM, LL>(wav, n_clips, L, hop, n_mels, tb, mp.max_pieces_per_seg <= GATHER_MAXP && n_mels <= 64, T_out, out, clip_max)
+#define GO3(RR, MM, LL) run<RR, MM, LL>(wav, n_clips, L, hop, n_mels, tb, mp.seg_major, T_out, out, clip_max)
 #define GO(RR)                                                                   \
     if (n_fft == 32 * RR) {                                                      \
         if (mode == MODE_FOA) { if (layout == 0) GO3(RR, MODE_FOA, 0); else GO3(RR, MODE_FOA, 1); } \
