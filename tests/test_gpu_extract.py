@@ -150,3 +150,21 @@ def test_on_the_fly_chunks_equal_full_clip_rows():
     transforms.mask_batch_(want, (24, 1), (16, 1), seed=11, sample_offset=40)
     assert torch.equal(batch, want)
     assert pipeline.clip_max_keys(cmax).equal(key)
+
+
+@pytest.mark.parametrize('mode', ['foa', 'mic'])
+def test_repeated_launches_are_bit_identical_across_layouts_of_work(mode):
+    """The two warps of a frame team hand data to each other through shared memory behind named barriers; a missing
+    barrier shows up as run-to-run differences.  Same input 4 times over a grid-filling shard, and once more as part of
+    a larger batch (different frame -> team assignment): every copy must be bit-identical."""
+    from seld_b200 import pipeline
+    from seld_b200.synth import make_clips
+    wav = make_clips(range(900, 906), 480 * 400).cuda()                      # 6 x 401 frames: every CTA gets several teams' worth
+    first, key0 = pipeline.extract_batch(wav, 24000, mode=mode, **PROD)
+    for _ in range(3):
+        again, key = pipeline.extract_batch(wav, 24000, mode=mode, **PROD)
+        assert torch.equal(again, first) and torch.equal(key, key0)
+    big = torch.cat([wav[3:], wav, wav[:2]])                                  # the same clips at other positions of a batch
+    out, key = pipeline.extract_batch(big, 24000, mode=mode, **PROD)
+    assert torch.equal(out[3:9], first) and torch.equal(key[3:9], key0)
+    assert torch.equal(out[:3], first[3:]) and torch.equal(out[9:], first[:2])
