@@ -1,8 +1,8 @@
 // Fused STFT -> log-mel + intensity-vector / GCC-PHAT extractor, sm_100a.
 //
 // Replaces reference feature_extractor.py:53-88 (extract_features) and the feature half of :117-149
-// (pad / truncate), batched over clips.  One warp owns one STFT frame of all four channels; see
-// extract_core.cuh for the per-warp algorithm.  Persistent CTAs (one per SM, limited by shared memory)
+// (pad / truncate), batched over clips.  A team of two warps owns one STFT frame of all four channels; see
+// extract_core.cuh for the per-lane algorithm.  Persistent CTAs (one per SM, limited by shared memory)
 // walk super-chunks of consecutive frames so that the 2.13x overlap between neighbouring frames is served
 // by L1/L2 and HBM sees every sample once.
 #include <math.h>
@@ -75,10 +75,10 @@ struct ExtractArgs {
     long long n_super;        // super-chunks of fsc frames
 };
 
-static int frames_per_warp() {   // frames a warp handles per super-chunk (SELD_FPW overrides, for experiments)
+static int frames_per_team() {   // consecutive frames a team handles per super-chunk (SELD_FPW overrides, for experiments)
     const char* e = getenv("SELD_FPW");
     const int n = e ? atoi(e) : 0;
-    return n > 0 ? n : 2;      // measured: 2 -> 11.53 ms, 4 -> 11.67, 8 -> 11.88, 16 -> 11.98 per 600 planar clips
+    return n > 0 ? n : 2;      // measured (600 planar FOA clips): 1 -> 11.59 ms, 2 -> 11.19, 3 -> 11.19, 4 -> 11.25, 8 -> 11.26
 }
 
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
@@ -310,7 +310,7 @@ template <int R, int MODE, int LAYOUT, bool EDGE, bool TC>
 static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream) {
     a.frames_per_clip = EDGE ? a.t_lo + (a.t_tot - a.t_hi) : a.t_hi - a.t_lo;
     if (a.frames_per_clip <= 0) return SELD_OK;
-    a.fpw = frames_per_warp();
+    a.fpw = frames_per_team();
     a.fsc = (plan->warps_per_cta / 2) * a.fpw;
     const long long per_super = a.fsc;
     a.n_super = ((long long)a.n_clips * a.frames_per_clip + per_super - 1) / per_super;
