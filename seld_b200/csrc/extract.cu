@@ -87,7 +87,7 @@ __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 template <int R, int MODE>
 __host__ __device__ constexpr int table_bytes(int n_mels) {
     using G = Geo<R>;
-    return align16(G::N * 8) + align16(G::TL * G::BPT * 8) + align16(G::TL * 8) + 2 * align16(G::TL * 4) + align16((n_mels + 2) * 4) + 64 +
+    return align16(G::N * 8) + align16(G::TL * G::BPT * 8) + align16(G::TL * 8) + 2 * align16(G::TL * 4) + align16((n_mels + 2) * 4) + 64 + 16 +
            align16(G::N * 4) + (MODE == MODE_MIC ? align16(G::N * 8) : 0);
 }
 // One frame team (two warps): an exchange buffer per warp (its spectrum overwrites it in place), the piece / GCC exchange
@@ -119,6 +119,9 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     const int team = warp >> 1;
     const int u = h * 32 + lane;              // lane within the team
     const int bar_id = 1 + team;              // named barrier of the team (0 is __syncthreads)
+    // per-lane constant tables (window, twiddles, mel weights) live in tensor memory in the hot kernel: tcgen05.ld keeps
+    // ~18 % of the shared-memory wavefronts off the LSU data pipe this kernel is bound by (extract_core.cuh)
+    constexpr bool TM = (R == 32) && !EDGE;
 
     // ---- CTA-shared tables
     unsigned char* p = smem;
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     int* s_slot1 = reinterpret_cast<int*>(p);  p += align16(TL * 4);
     int* s_pb = reinterpret_cast<int*>(p);  p += align16((a.n_mels + 2) * 4);
     float2* s_zero = reinterpret_cast<float2*>(p);  p += 64;
+    unsigned& s_tmem_base = *reinterpret_cast<unsigned*>(p);  p += 16;      // TMEM allocation of this CTA
     float* s_win = reinterpret_cast<float*>(p);  p += align16(G::N * 4);
     float2* s_tw_lin = nullptr;
     if constexpr (MODE == MODE_MIC) { s_tw_lin = reinterpret_cast<float2*>(p);  p += align16(G::N * 8); }
@@ -146,6 +150,43 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
         s_slot1[threadIdx.x] = a.slot1[threadIdx.x];
     }
     if (threadIdx.x < 8) s_zero[threadIdx.x] = make_float2(0.f, 0.f);
+    unsigned taddr = 0;
+    if constexpr (TM) {
+        static_assert(!TM || 2 * G::BPT <= 32, "mel weights of a lane must fit 32 TMEM columns");
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(static_cast<unsigned>(__cvta_generic_to_shared(&s_tmem_base))), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        taddr = s_tmem_base + ((32u * (warp & 3)) << 16);
+        if (warp < 4) {                           // one writer per TMEM lane quadrant
+            float r[16];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = a.window[lane + 32 * (16 * c + i)] * wscale;
+                tmem_st16(taddr + TMEM_COL_WIN + 16 * c, r);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float2 t = a.tw_t[(8 * g + i) * 32 + lane]; r[2 * i] = t.x; r[2 * i + 1] = t.y; }
+                tmem_st16(taddr + TMEM_COL_TW + 16 * g, r);
+            }
+            const float* w01 = reinterpret_cast<const float*>(a.w01) + size_t(u) * (2 * G::BPT);     // u: quadrant parity == warp parity
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = (16 * c + i < 2 * G::BPT) ? w01[16 * c + i] : 0.f;
+                tmem_st16(taddr + TMEM_COL_W01 + 16 * c, r);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+    }
     // ---- per-team regions
     unsigned char* tp = p + size_t(team) * team_bytes<R, MODE>(a.n_mels, a.e_bytes);
     float2* S0 = reinterpret_cast<float2*>(tp);  tp += align16(G::E_ELEMS * 8);     // warp 0: exchange, then spectrum of pair 0
@@ -156,6 +197,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     const int row_elems = a.n_mels * C;
     for (int i = u; i < a.x_zero_f2; i += TL) X[i] = make_float2(0.f, 0.f);    // segment-major slots without a piece stay zero
     __syncthreads();
+    if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
     // window taps of this lane: s_win[lane + 32 n2].  The interior kernel reads them from shared memory per frame (at 168
     // registers per thread a register copy would be spilled to local memory anyway); the edge kernel keeps a copy.
     const float* wlane = s_win + lane;
@@ -170,7 +212,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     auto finish_frame = [&](int clip, int t, float* row) {
         constexpr bool tc = TC && MODE == MODE_MIC && R == 32;       // tensor-core GCC: this kernel only writes phasor rows
         team_bar(bar_id);                                            // both spectra are in place
-        bin_phase<R, MODE, tc>(S0, S1, tb, X, 1e-8f, u);
+        bin_phase<R, MODE, tc, TM>(S0, S1, tb, X, 1e-8f, u, taddr + TMEM_COL_W01);
         team_bar(bar_id);
         float mx = a.seg_major ? gather_lanes<MODE>(X, acc, a.n_mels, u) : gather_phase<MODE>(X, tb, acc, a.n_mels, u);
         if constexpr (MODE == MODE_MIC && !tc) {
@@ -284,14 +326,23 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
 #pragma unroll 1
         while (g >= 0) {
             float2 v[R];
-            if constexpr (LAYOUT == LAYOUT_PCM16_LC) apply_window_pcm16<R, 32>(raw, 0, wlane, v);
-            else apply_window<R, 32>(raw, wlane, v);
+            if constexpr (TM) {
+                float w[R];
+                tmem_ld16(taddr + TMEM_COL_WIN, w);
+                tmem_ld16(taddr + TMEM_COL_WIN + 16, w + 16);
+                if constexpr (LAYOUT == LAYOUT_PCM16_LC) apply_window_pcm16<R>(raw, 0, w, v);
+                else apply_window<R>(raw, w, v);
+            } else {
+                if constexpr (LAYOUT == LAYOUT_PCM16_LC) apply_window_pcm16<R, 32>(raw, 0, wlane, v);
+                else apply_window<R, 32>(raw, wlane, v);
+            }
             const int clip_now = clip, t_now = t;
             float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
             if (++fi == a.fpw || team * a.fpw + fi >= a.fsc) { fi = 0; sc += sc_step; }
             const long long g_next = frame_index(sc, fi);
             if (g_next >= 0) request(g_next);
-            stage1_fft_store<R>(v, tb, E, lane);
+            if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
+            else stage1_fft_store<R>(v, tb, E, lane);
             __syncwarp();
             stage2_forward<R>(E, E, lane);
             finish_frame(clip_now, t_now, row);
@@ -299,6 +350,11 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
         }
     }
     if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], float_to_key(run_max));
+    if constexpr (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem_base), "r"(TMEM_COLS));
+    }
 }
 
 __global__ void clip_max_decode_kernel(const unsigned int* keys, int n, float* out) {

@@ -274,6 +274,56 @@ SELD_HD void stage1_fft_store(float2* v, const Tables& tb, float2* E, int lane) 
     }
 }
 
+// ---------------------------------------------------------------- per-lane constant tables in tensor memory
+// The window taps, the stage-1 twiddles and the mel weights are PER-LANE constants: lane l only ever reads its own
+// column of each table.  That is exactly the access tensor memory offers a warp (warp w reads TMEM lanes 32 (w % 4) ..
+// +31, thread i <-> lane i), and tcgen05.ld does not go through the LSU / shared-memory data pipe this kernel is bound
+// by.  Column map of a lane (n_fft = 1024): [0, 32) window taps w[l + 32 n2]; [32, 96) twiddles (re, im) of W^(l k2),
+// k2 < 32; [96, 114) mel weights (w0, w1) of team lane u's 9 bins.  Quadrants 0/2 hold the tables of a team's first
+// warp, 1/3 those of its second (warp parity == quadrant parity).
+#if defined(__CUDACC__)
+constexpr int TMEM_COL_WIN = 0, TMEM_COL_TW = 32, TMEM_COL_W01 = 96, TMEM_COLS = 128;
+
+__device__ __forceinline__ void tmem_ld2(unsigned taddr, float& a, float& b) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=f"(a), "=f"(b) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
+                   "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const float* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :: "r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]), "f"(r[8]),
+                    "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]) : "memory");
+}
+
+// stage1_fft_store with the twiddles read from tensor memory (same values, same arithmetic as the shared-table version)
+template <int R>
+__device__ __forceinline__ void stage1_fft_store_tm(float2* v, unsigned taddr_tw, float2* E, int lane) {
+    using G = Geo<R>;
+    static_assert(R % 8 == 0, "twiddles are fetched 8 at a time");
+    pfft_dif<R>(v);
+    float4* E4 = reinterpret_cast<float4*>(E + lane * G::EP);
+#pragma unroll
+    for (int g = 0; g < R / 8; ++g) {
+        float t[16];                                   // (re, im) of k2 = 8g .. 8g + 7
+        tmem_ld16(taddr_tw + 16 * g, t);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * g + jj;
+            const int p0 = bitrev(2 * j, G::LOG2R), p1 = bitrev(2 * j + 1, G::LOG2R);
+            const float2 a = pcmul(v[p0], t[4 * jj], t[4 * jj + 1]), b = pcmul(v[p1], t[4 * jj + 2], t[4 * jj + 3]);
+            float4 q; q.x = a.x; q.y = a.y; q.z = b.x; q.w = b.y;
+            E4[j] = q;
+        }
+    }
+}
+#endif
+
 template <int R, int LAYOUT>
 SELD_HD void stage1_forward(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, const float* wreg,
                             const Tables& tb, float2* E, int lane) {
@@ -425,8 +475,9 @@ SELD_HD float pack_half2(float lo, float hi) {          // two floats -> one 32-
 // GCC_TC (MIC only): instead of per-channel unit phasors for the CUDA-core inverse transforms, write the six PAIR
 // phasors exp(i angle(conj(X_m) X_n)) as fp16 (re, im) words into the bin's own four spectrum slots -- the A operand
 // rows of the tensor-core lag projection (gcc_gemm.cu), copied out by gcc_tc_copy_out.
-template <int R, int MODE, bool GCC_TC = false>
-SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, float eps, int u) {     // u: team lane, 0..TL-1
+template <int R, int MODE, bool GCC_TC = false, bool W_TMEM = false>
+SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, float eps, int u,      // u: team lane, 0..TL-1
+                       unsigned taddr_w01 = 0) {                                                    // W_TMEM: mel weights from tensor memory
     using G = Geo<R>;
     constexpr int N = G::N;
     constexpr int NV = PieceGeo<MODE>::NV;
@@ -491,7 +542,14 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
                 }
             }
         }
-        const float2 w = tb.w01[kbeg + i];
+        float2 w;
+#if defined(__CUDA_ARCH__)
+        if constexpr (W_TMEM) tmem_ld2(taddr_w01 + 2 * i, w.x, w.y);
+        else w = tb.w01[kbeg + i];
+#else
+        (void)taddr_w01;
+        w = tb.w01[kbeg + i];
+#endif
 #pragma unroll
         for (int c = 0; c < NV; ++c) acc2[c] = pfma(make_float2(val[c], val[c]), w, acc2[c]);
         const unsigned flag = static_cast<unsigned>(endmask >> i) & 1u;
