@@ -186,6 +186,14 @@ SELD_API int seld_channel_remap(const float* in_dev, float* out_dev, int64_t n_s
                                 const int32_t* table_dev, void* stream);
 
 /*
+ * Per-sample level jitter (reference trainv2.py:120-124, `random_ups_and_downs`: one N(0, 0.2^2) scalar added to the four
+ * log-mel channels of a sample): out[b, p, c] = in[b, p, c] + (c < n_first ? offset[b] : 0) for float32
+ * [n_samples][positions][n_chan]; offset_dev float32 [n_samples].  in_dev == out_dev is allowed.
+ */
+SELD_API int seld_channel_offset(const float* in_dev, float* out_dev, int64_t n_samples, int64_t positions, int n_chan, int n_first,
+                                 const float* offset_dev, void* stream);
+
+/*
  * Stand-alone stages (API parity with the reference's public helpers; the hot path is seld_extract).
  *   seld_complex_spec     reference feature_extractor.py:153-173; spec_dev [n_chan][T][F] complex64 (frame-major;
  *                         the Python wrapper returns the [C, F, T] transposed view)

@@ -239,3 +239,40 @@ extern "C" int seld_channel_remap(const float* in_dev, float* out_dev, int64_t n
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Per-sample level jitter: out[b, p, c] = in[b, p, c] + (c < n_first ? offset[b] : 0) -- the data movement of the
+// reference's `random_ups_and_downs` (trainv2.py:120-124: one N(0, 0.2^2) scalar added to the 4 log-mel channels of a
+// sample, ahead of the masks).  Out of place it doubles as the copy the masking transform needs anyway; in == out works.
+namespace seld {
+__global__ void __launch_bounds__(256) channel_offset_kernel(const float* __restrict__ in, float* __restrict__ out, unsigned per_sample,
+                                                             unsigned C, unsigned n_first, const float* __restrict__ offset) {
+    const long long b = blockIdx.y;
+    const float off = offset[b];
+    const float* src = in + b * per_sample;
+    float* dst = out + b * per_sample;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < per_sample; e += gridDim.x * blockDim.x) {
+        const unsigned c = e % C;
+        dst[e] = src[e] + (c < n_first ? off : 0.f);
+    }
+}
+}  // namespace seld
+
+extern "C" int seld_channel_offset(const float* in_dev, float* out_dev, int64_t n_samples, int64_t positions, int n_chan, int n_first,
+                                   const float* offset_dev, void* stream) {
+    if (!in_dev || !out_dev || !offset_dev || n_samples < 0 || positions < 0 || n_chan < 1 || n_first < 0 || n_first > n_chan) {
+        set_error("bad argument");
+        return SELD_EINVAL;
+    }
+    const long long per_sample = positions * n_chan;
+    if (per_sample >= (1ll << 31) || n_samples > 65535) { set_error("sample too large (2^31 elements) or more than 65535 samples"); return SELD_EUNSUPPORTED; }
+    if (per_sample == 0 || n_samples == 0) return SELD_OK;
+    long long bx = (per_sample + 255) / 256;
+    const long long cap = (148ll * 16 + n_samples - 1) / n_samples;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    dim3 grid((unsigned)bx, (unsigned)n_samples);
+    channel_offset_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_dev, out_dev, (unsigned)per_sample, (unsigned)n_chan,
+                                                                             (unsigned)n_first, offset_dev);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}

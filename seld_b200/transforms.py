@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 
-__all__ = ['mask', 'simple_mask', 'mask_batch_', 'sample_masks', 'set_seed', 'set_counter_seed', 'foa_intensity_vec_aug', 'acs_aug',
+__all__ = ['mask', 'simple_mask', 'mask_batch_', 'sample_masks', 'random_ups_and_downs', 'set_seed', 'set_counter_seed', 'foa_intensity_vec_aug', 'acs_aug',
            'mic_gcc_perm', 'channel_list', 'split_total_labels_to_sed_doa']
 
 _MAXINT32 = 2 ** 31 - 1
@@ -173,12 +173,53 @@ def mask_batch_(x, time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, 
                    _lib.RNG_PHILOX_COUNTER, None, return_draws)
 
 
-def sample_masks(time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None):
-    """The reference's per-sample masking lambdas (train.py:157-160: ``mask(x, axis=-3, max_mask_size=24, n_mask=1)`` then
-    ``mask(x, axis=-2, max_mask_size=16)``) as ONE batched transform for ``data_loader.seldnet_data_to_dataloader``:
-    ``(x [B, T, F, C], y) -> (masked copy of x, y)``, independent draws per sample, one fused launch per batch."""
+STREAM_LEVEL_JITTER = 0x102
+
+
+def _level_offsets(n, stddev, seed, sample_offset):
+    """One N(0, stddev^2) float32 per sample: Box-Muller (float64) on Philox words 0, 1 of (sample, STREAM_LEVEL_JITTER)."""
+    from . import philox
+    seed, first = _draw_seed(n, seed, sample_offset)
+    w = philox.sample_words(seed, first, n, STREAM_LEVEL_JITTER).astype(np.float64)
+    u1, u2 = (w[:, 0] + 0.5) / 4294967296.0, (w[:, 1] + 0.5) / 4294967296.0
+    return (stddev * np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)).astype(np.float32)
+
+
+def _offset_copy(x, offsets, n_first):
+    """New tensor: x[b, ..., c] + offsets[b] for c < n_first (one pass; also the copy the masks need)."""
+    _lib.require_device()
+    xs = x.to(dtype=torch.float32).contiguous()
+    out = torch.empty_like(xs)
+    off = torch.as_tensor(np.ascontiguousarray(offsets, dtype=np.float32), device=xs.device)
+    b, c = xs.shape[0], xs.shape[-1]
+    with torch.cuda.device(xs.device):
+        _lib.check(_lib.load().seld_channel_offset(_lib.ptr(xs), _lib.ptr(out), b, xs[0].numel() // c, c, int(n_first),
+                                                   _lib.ptr(off), _lib.current_stream_ptr()))
+    return out
+
+
+def random_ups_and_downs(x, y, stddev=0.2, seed=None, sample_offset=None, return_draws=False):
+    """reference trainv2.py:120-124: add ONE N(0, 0.2^2) scalar to channels [:4] (the log-mel block).  The reference maps
+    it over single samples [T, F, C]; here x may also be a batch [B, T, F, C] (one independent scalar per sample)."""
+    xt = torch.as_tensor(x)
+    single = xt.dim() == 3
+    xb = (xt.unsqueeze(0) if single else xt).cuda()
+    offs = _level_offsets(xb.shape[0], stddev, seed, sample_offset)
+    out = _offset_copy(xb, offs, min(4, xb.shape[-1]))
+    out = out[0] if single else out
+    return (out, y, offs) if return_draws else (out, y)
+
+
+def sample_masks(time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, level_jitter=None):
+    """The reference's per-sample transforms (train.py:157-160: ``mask(x, axis=-3, max_mask_size=24, n_mask=1)`` then
+    ``mask(x, axis=-2, max_mask_size=16)``; trainv2.py:134-138 puts ``random_ups_and_downs`` in front: ``level_jitter=0.2``)
+    as ONE batched transform for ``data_loader.seldnet_data_to_dataloader``: ``(x [B, T, F, C], y) -> (new x, y)``,
+    independent draws per sample; the level jitter rides on the copy the masks need, then one fused masking launch."""
     def op(x, y):
-        out = x.clone(memory_format=torch.contiguous_format)
+        if level_jitter:
+            out = _offset_copy(x, _level_offsets(x.shape[0], float(level_jitter), seed, None), min(4, x.shape[-1]))
+        else:
+            out = x.clone(memory_format=torch.contiguous_format)
         mask_batch_(out, time_mask, freq_mask, period=period, seed=seed)
         return out, y
     op.batched = True

@@ -79,3 +79,13 @@ def test_host_philox_matches_oracle_generator():
         s = (1 << 32) - 2 + i
         want = philox4x32_10((s & 0xFFFFFFFF, s >> 32, T.STREAM_IV_AUG, 3), (seed & 0xFFFFFFFF, seed >> 32))
         assert tuple(int(v) for v in w[i]) == want
+
+
+def test_level_jitter_draws_are_normal_and_reproducible():
+    a = T._level_offsets(100000, 0.2, seed=11, sample_offset=5)
+    b = T._level_offsets(100000, 0.2, seed=11, sample_offset=5)
+    assert a.dtype == np.float32 and np.array_equal(a, b)
+    assert abs(float(a.mean())) < 3e-3 and abs(float(a.std()) - 0.2) < 2e-3
+    assert abs(float(np.mean(np.abs(a) < 0.2)) - 0.6827) < 5e-3              # one sigma
+    # keyed by global sample index: a shifted window sees the same values
+    assert np.array_equal(T._level_offsets(10, 0.2, seed=11, sample_offset=15), a[10:20])

@@ -62,3 +62,33 @@ def test_channel_remap_errors():
     assert lib.seld_channel_remap(_lib.ptr(x), _lib.ptr(o), 0, 3, 4, 1, _lib.ptr(p), None) == 0
     with pytest.raises(ValueError):
         T.foa_intensity_vec_aug(torch.zeros(1, 2, 3, 6), torch.zeros(1, 2, 12))
+
+
+def test_random_ups_and_downs_adds_one_scalar_to_the_logmel_channels():
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(6, 300, 64, 7, generator=g) - 0.5
+    nx, y, offs = T.random_ups_and_downs(x.cuda(), 'labels', seed=21, sample_offset=3, return_draws=True)
+    assert y == 'labels' and offs.shape == (6,) and len(set(offs.tolist())) == 6
+    want = x.numpy().copy()
+    want[..., :4] += offs[:, None, None, None]                                    # reference trainv2.py:120-124
+    assert np.array_equal(nx.cpu().numpy(), want)
+    one, _ = T.random_ups_and_downs(x[2].cuda(), None, seed=21, sample_offset=5)     # single sample [T, F, C], same draw as sample 2
+    assert np.array_equal(one.cpu().numpy(), want[2])
+
+
+def test_sample_masks_with_level_jitter():
+    x = (torch.rand(8, 300, 64, 7) + 1.0).cuda()
+    T.set_counter_seed(77)
+    op = T.sample_masks(time_mask=(6, 10), freq_mask=(8, 6), level_jitter=0.2)         # trainv2.py:134-138
+    out, y = op(x, None)
+    assert out.data_ptr() != x.data_ptr() and float(x.min()) >= 1.0
+    masked = out == 0
+    assert bool(masked.any()) and float(masked.float().mean()) < 0.6
+    d = (out - x)[~masked]
+    assert float(d.abs().max()) < 1.5
+    for b in range(8):                                                             # per sample: one offset on channels 0..3, none on 4..6
+        keep = ~masked[b]
+        lo = (out[b] - x[b])[..., :4][keep[..., :4]]
+        hi = (out[b] - x[b])[..., 4:][keep[..., 4:]]
+        assert float(hi.abs().max()) == 0.0
+        assert float(lo.max() - lo.min()) < 1e-6
