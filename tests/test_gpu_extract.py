@@ -170,8 +170,9 @@ def test_repeated_launches_are_bit_identical_across_layouts_of_work(mode):
     assert torch.equal(out[:3], first[3:]) and torch.equal(out[9:], first[:2])
 
 
-def test_dev_set_size_properties():
-    """BASELINE.json configs[1] at full size (600 x 60 s clips, 13.8 GB resident) through size-independent properties:
+@pytest.mark.parametrize('mode', ['foa', 'mic'])
+def test_dev_set_size_properties(mode):
+    """BASELINE.json configs[1] / [2] at full size (600 x 60 s clips, 13.8 GB resident) through size-independent properties:
     (1) every copy of a clip in the shard gives bit-identical rows wherever it sits; (2) hop-shift equivariance -- a clip
     advanced by one hop reproduces the interior rows of the original one frame later, bit for bit; (3) the dataset
     statistics of the tiled shard equal those of its 8 distinct clips; (4) normalised output has zero mean / unit std."""
@@ -184,7 +185,8 @@ def test_dev_set_size_properties():
     n = 600
     wav = torch.stack([base[i % 8] for i in range(n)])
     assert wav.shape == (n, 4, 1_440_000)
-    feat, key = pipeline.extract_batch(wav, 24000, mode='foa', t_out=3000, **PROD)
+    n_ch = 7 if mode == 'foa' else 10
+    feat, key = pipeline.extract_batch(wav, 24000, mode=mode, t_out=3000, **PROD)
     del wav
     for i in range(8, n):                                                       # (1)
         assert torch.equal(feat[i], feat[i % 8]), i
@@ -192,10 +194,10 @@ def test_dev_set_size_properties():
     assert torch.equal(feat[7, 2:2990], feat[0, 3:2991])                        # (2)
     acc_all = pipeline.partial_statistics(feat, key, 3001)                      # (3)
     acc_8 = pipeline.partial_statistics(feat[:8].contiguous(), key[:8].contiguous(), 3001)
-    m_all, s_all = pipeline.finish_statistics(acc_all, 64, 7)
-    m_8, s_8 = pipeline.finish_statistics(acc_8, 64, 7)
+    m_all, s_all = pipeline.finish_statistics(acc_all, 64, n_ch)
+    m_8, s_8 = pipeline.finish_statistics(acc_8, 64, n_ch)
     assert float((m_all - m_8).abs().max()) <= 1e-5 and float((s_all - s_8).abs().max()) <= 1e-5
     pipeline.finalize_(feat, key, 3001, m_all, s_all)                           # (4)
-    flat = feat.view(-1, 64 * 7).double()
+    flat = feat.view(-1, 64 * n_ch).double()
     assert float(flat.mean(dim=0).abs().max()) <= 2e-4
     assert float((flat.std(dim=0, unbiased=False) - 1).abs().max()) <= 2e-4
