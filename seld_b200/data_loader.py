@@ -15,7 +15,8 @@ drop-remainder rule follow the reference; random streams are this package's own 
 import numpy as np
 import torch
 
-__all__ = ['data_loader', 'seldnet_data_to_dataloader', 'frame_windows', 'overlap_and_add_mean', 'ensemble_outputs']
+__all__ = ['data_loader', 'seldnet_data_to_dataloader', 'get_preprocessed_x', 'frame_windows', 'overlap_and_add_mean',
+           'ensemble_outputs']
 
 
 def _as_tensor(a, device):
@@ -136,6 +137,22 @@ def seldnet_data_to_dataloader(features, labels, train=True, label_window_size=6
         shuffle = n_samples // batch_size if shuffle_size is None else shuffle_size
     return _BatchIterable(xs, ys, n_samples, batch_size, loop_time if train else 1, kwargs.get('sample_transforms'),
                           kwargs.get('batch_transforms'), shuffle, seed)
+
+
+def get_preprocessed_x(wav, sample_rate, mode='foa', n_mels=64, multiplier=5, max_label_length=600, **kwargs):
+    """reference data_loader.py:268-308 (the on-the-fly extractor behind ``get_tdm_dataset``): features of one clip
+    ``wav [4, L]`` (or a batch ``[n, 4, L]``), top_db-clamped, zero-padded / truncated to ``max_label_length * multiplier``
+    frames -> CUDA float32 ``[max_len, n_mels, C]`` (``[n, max_len, n_mels, C]`` for a batch).  One fused launch + the clamp;
+    the reference's numpy-or-tensor return type becomes a device tensor."""
+    from . import pipeline
+    w = torch.as_tensor(wav)
+    single = w.dim() == 2
+    w = (w.unsqueeze(0) if single else w).to(device='cuda', dtype=torch.float32).contiguous()
+    max_len = int(max_label_length) * int(multiplier)
+    feat, key = pipeline.extract_batch(w, sample_rate, mode=mode, n_mels=n_mels, t_out=max_len, **kwargs)
+    hop = kwargs.get('hop_length') or (kwargs.get('win_length') or kwargs.get('n_fft', 512)) // 2
+    pipeline.finalize_(feat, key, 1 + w.shape[-1] // hop)
+    return feat[0] if single else feat
 
 
 # --------------------------------------------------------------------------- sliding-window evaluation (trainv2.py:158-192)

@@ -56,3 +56,21 @@ def test_sliding_window_framing_on_device():
     w = DL.frame_windows(x, 300, 5)
     assert tuple(w.shape) == (541, 300, 64, 7) and w.data_ptr() == x.data_ptr()
     assert torch.equal(w[17], x[85:385])
+
+
+@pytest.mark.parametrize('mode', ['foa', 'mic'])
+def test_get_preprocessed_x_matches_oracle(mode):
+    """reference data_loader.py:268-308 = extract_features + pad / truncate to max_label_length * multiplier frames."""
+    from oracle import extractor as O
+    from seld_b200.synth import make_clips
+    from cases import PROD, check_features
+    wav = make_clips(range(40, 42), 24000 * 4)                                  # 4 s -> 201 frames
+    for max_label in (30, 50):                                                   # truncate to 150, pad to 250
+        got = DL.get_preprocessed_x(wav[0], 24000, mode=mode, max_label_length=max_label, multiplier=5, **PROD)
+        ref = O.extract_features_port(wav[0], 24000, mode=mode, **PROD)
+        want = O.preprocess_features_port(ref, max_label_length=max_label, multiplier=5)
+        assert tuple(got.shape) == want.shape == (max_label * 5, 64, 7 if mode == 'foa' else 10)
+        check_features(got.cpu().numpy(), want, mode, f'{mode} {max_label}')
+    both = DL.get_preprocessed_x(wav, 24000, mode=mode, max_label_length=30, **PROD)
+    assert tuple(both.shape)[:2] == (2, 150)
+    assert torch.equal(both[0], DL.get_preprocessed_x(wav[0], 24000, mode=mode, max_label_length=30, **PROD))
