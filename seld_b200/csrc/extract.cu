@@ -59,9 +59,10 @@ struct ExtractArgs {
     const unsigned long long* endmask;
     const int* slot0;
     const int* slot1;
+    const int* ov;
     const int* pb;
     int hop, n_mels;
-    int e_bytes;              // per-team piece / GCC exchange buffer size
+    int x_bytes;              // per-team piece / GCC exchange buffer size (SmemPlan::x_bytes)
     int seg_major;            // piece records in the segment-major layout: gather_lanes (else the compact layout + gather_phase)
     int x_zero_f2;            // float2 elements of the piece buffer that must read as zero where no piece is stored
     int gcc_tc;               // MIC: write fp16 pair phasors to gcc_rows; the tensor-core GEMM does the lag projection
@@ -83,32 +84,44 @@ static int frames_per_team() {   // consecutive frames a team handles per super-
 
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 
-// CTA-shared tables: lane-contiguous twiddles, mel pieces, and (MIC only) the linear twiddle table
-template <int R, int MODE>
-__host__ __device__ constexpr int table_bytes(int n_mels) {
+// Shared-memory plan of one kernel variant.  CTA-shared tables first, then one region per frame team (two warps): an
+// exchange buffer per warp (its spectrum overwrites it in place), the piece / GCC exchange buffer, the staged output row.
+// n_fft = 1024 keeps the per-lane constant tables in tensor memory, so only the small index tables stay here.
+template <int R, int MODE, bool TC>
+struct SmemPlan {
     using G = Geo<R>;
-    return align16(G::N * 8) + align16(G::TL * G::BPT * 8) + align16(G::TL * 8) + 2 * align16(G::TL * 4) + align16((n_mels + 2) * 4) + 64 + 16 +
-           align16(G::N * 4) + (MODE == MODE_MIC ? align16(G::N * 8) : 0);
-}
-// One frame team (two warps): an exchange buffer per warp (its spectrum overwrites it in place), the piece / GCC exchange
-// buffer, and the staged output row.
-template <int R, int MODE>
-__host__ __device__ constexpr int team_bytes(int n_mels, int e_bytes) {
-    using G = Geo<R>;
-    return 2 * align16(G::E_ELEMS * 8) + e_bytes + align16(n_mels * (MODE == MODE_FOA ? 7 : 10) * 4);
-}
+    static constexpr bool TM = (R == 32);                               // per-lane constants in tensor memory
+    static constexpr bool tc = TC && MODE == MODE_MIC && R == 32;       // tensor-core GCC: this kernel only writes phasor rows
+    static constexpr bool NEED_TW = !TM || (MODE == MODE_MIC && !tc);   // stage-1 twiddles (also the fast CUDA-core GCC stage 2)
+    static constexpr bool NEED_W01 = !TM;
+    static constexpr bool NEED_WIN = !TM;
+    static constexpr bool NEED_TWLIN = (MODE == MODE_MIC && !tc);
+    __host__ __device__ static constexpr int table_bytes(int n_mels) {
+        return (NEED_TW ? align16(G::N * 8) : 0) + (NEED_W01 ? align16(G::TL * G::BPT * 8) : 0) + align16(G::TL * 8) + 2 * align16(G::TL * 4) +
+               align16((n_mels + 2) * 4) + align16(64 * 4) + 16 + (NEED_WIN ? align16(G::N * 4) : 0) + (NEED_TWLIN ? align16(G::N * 8) : 0);
+    }
+    __host__ __device__ static constexpr int x_bytes(int n_slots) {
+        const int pieces = align16(n_slots * PieceGeo<MODE>::PSTRIDE * 8);
+        const int exchange = (MODE == MODE_MIC && !tc) ? align16(G::E_ELEMS * 8) : 0;
+        return pieces > exchange ? pieces : exchange;
+    }
+    __host__ __device__ static constexpr int team_bytes(int n_mels, int xb) {
+        return 2 * align16(G::E_ELEMS * 8) + xb + align16(n_mels * (MODE == MODE_FOA ? 7 : 10) * 4);
+    }
+};
 
-// Warps per CTA.  n_fft = 1024: 12 warps = 6 teams (168 registers per thread; three warps per scheduler hide the
-// shared-memory and dependent-issue latency that two could not -- measured 2 -> 4 -> 8 warps: 35 -> 17.7 -> 11.5 ms).
-template <int R>
-__host__ __device__ constexpr int max_warps() { return R <= 16 ? 16 : (R == 32 ? 12 : 4); }
+// Warps per CTA.  n_fft = 1024: up to 16 warps = 8 teams at 128 registers per thread (four warps per scheduler; measured
+// 2 -> 4 -> 8 warps with whole frames per warp: 35 -> 17.7 -> 11.5 ms, then teams of two: 12 warps 9.9 ms).
+// (MIC keeps 12: its bin phase is register-hungrier and measured 1.5 % slower at 128 registers.)
+template <int R, int MODE>
+__host__ __device__ constexpr int max_warps() { return R <= 16 ? 16 : (R == 32 ? (MODE == MODE_FOA ? 16 : 12) : 4); }
 
 __device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
 
 // EDGE = false: interior frames only, loads specialised on LAYOUT (the hot kernel).
 // EDGE = true : the few frames per clip that need reflection, plus the zero padding rows (generic strided loads).
 template <int R, int MODE, int LAYOUT, bool EDGE, bool TC>
-__global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(ExtractArgs a) {
+__global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(ExtractArgs a) {
     using G = Geo<R>;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
     constexpr int TL = G::TL;
@@ -119,37 +132,40 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
     const int team = warp >> 1;
     const int u = h * 32 + lane;              // lane within the team
     const int bar_id = 1 + team;              // named barrier of the team (0 is __syncthreads)
-    // per-lane constant tables (window, twiddles, mel weights) live in tensor memory in the hot kernel: tcgen05.ld keeps
+    // per-lane constant tables (window, twiddles, mel weights) live in tensor memory for n_fft = 1024: tcgen05.ld keeps
     // ~18 % of the shared-memory wavefronts off the LSU data pipe this kernel is bound by (extract_core.cuh)
-    constexpr bool TM = (R == 32) && !EDGE;
-
+    using SP = SmemPlan<R, MODE, TC>;
+    constexpr bool TM = SP::TM;
     // ---- CTA-shared tables
     unsigned char* p = smem;
-    float2* s_tw_t = reinterpret_cast<float2*>(p);  p += align16(G::N * 8);
-    float2* s_w01 = reinterpret_cast<float2*>(p);  p += align16(TL * G::BPT * 8);
+    float2* s_tw_t = nullptr;
+    if constexpr (SP::NEED_TW) { s_tw_t = reinterpret_cast<float2*>(p);  p += align16(G::N * 8); }
+    float2* s_w01 = nullptr;
+    if constexpr (SP::NEED_W01) { s_w01 = reinterpret_cast<float2*>(p);  p += align16(TL * G::BPT * 8); }
     unsigned long long* s_endmask = reinterpret_cast<unsigned long long*>(p);  p += align16(TL * 8);
     int* s_slot0 = reinterpret_cast<int*>(p);  p += align16(TL * 4);
     int* s_slot1 = reinterpret_cast<int*>(p);  p += align16(TL * 4);
     int* s_pb = reinterpret_cast<int*>(p);  p += align16((a.n_mels + 2) * 4);
-    float2* s_zero = reinterpret_cast<float2*>(p);  p += 64;
+    int* s_ov = reinterpret_cast<int*>(p);  p += align16(64 * 4);
     unsigned& s_tmem_base = *reinterpret_cast<unsigned*>(p);  p += 16;      // TMEM allocation of this CTA
-    float* s_win = reinterpret_cast<float*>(p);  p += align16(G::N * 4);
+    float* s_win = nullptr;
+    if constexpr (SP::NEED_WIN) { s_win = reinterpret_cast<float*>(p);  p += align16(G::N * 4); }
     float2* s_tw_lin = nullptr;
-    if constexpr (MODE == MODE_MIC) { s_tw_lin = reinterpret_cast<float2*>(p);  p += align16(G::N * 8); }
+    if constexpr (SP::NEED_TWLIN) { s_tw_lin = reinterpret_cast<float2*>(p);  p += align16(G::N * 8); }
     const float wscale = ((EDGE ? a.layout : LAYOUT) == LAYOUT_PCM16_LC) ? (1.0f / 32768.0f) : 1.0f;    // exact: folds the PCM decode
     for (int i = threadIdx.x; i < G::N; i += blockDim.x) {
-        s_win[i] = a.window[i] * wscale;
-        s_tw_t[i] = a.tw_t[i];
-        if constexpr (MODE == MODE_MIC) s_tw_lin[i] = a.tw_lin[i];
+        if constexpr (SP::NEED_WIN) s_win[i] = a.window[i] * wscale;
+        if constexpr (SP::NEED_TW) s_tw_t[i] = a.tw_t[i];
+        if constexpr (SP::NEED_TWLIN) s_tw_lin[i] = a.tw_lin[i];
     }
-    for (int i = threadIdx.x; i < TL * G::BPT; i += blockDim.x) s_w01[i] = a.w01[i];
+    if constexpr (SP::NEED_W01) { for (int i = threadIdx.x; i < TL * G::BPT; i += blockDim.x) s_w01[i] = a.w01[i]; }
     for (int i = threadIdx.x; i < a.n_mels + 2; i += blockDim.x) s_pb[i] = a.pb[i];
     if (threadIdx.x < TL) {
         s_endmask[threadIdx.x] = a.endmask[threadIdx.x];
         s_slot0[threadIdx.x] = a.slot0[threadIdx.x];
         s_slot1[threadIdx.x] = a.slot1[threadIdx.x];
+        s_ov[threadIdx.x] = a.ov[threadIdx.x];
     }
-    if (threadIdx.x < 8) s_zero[threadIdx.x] = make_float2(0.f, 0.f);
     unsigned taddr = 0;
     if constexpr (TM) {
         static_assert(!TM || 2 * G::BPT <= 32, "mel weights of a lane must fit 32 TMEM columns");
@@ -188,21 +204,19 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
         asm volatile("tcgen05.fence::before_thread_sync;");
     }
     // ---- per-team regions
-    unsigned char* tp = p + size_t(team) * team_bytes<R, MODE>(a.n_mels, a.e_bytes);
+    unsigned char* tp = p + size_t(team) * SP::team_bytes(a.n_mels, a.x_bytes);
     float2* S0 = reinterpret_cast<float2*>(tp);  tp += align16(G::E_ELEMS * 8);     // warp 0: exchange, then spectrum of pair 0
     float2* S1 = reinterpret_cast<float2*>(tp);  tp += align16(G::E_ELEMS * 8);     // warp 1: exchange, then spectrum of pair 1
-    float2* X = reinterpret_cast<float2*>(tp);  tp += a.e_bytes;                    // mel pieces, then GCC exchange
+    float2* X = reinterpret_cast<float2*>(tp);  tp += a.x_bytes;                    // mel pieces, then GCC exchange
     float* acc = reinterpret_cast<float*>(tp);
     float2* E = h ? S1 : S0;
     const int row_elems = a.n_mels * C;
     for (int i = u; i < a.x_zero_f2; i += TL) X[i] = make_float2(0.f, 0.f);    // segment-major slots without a piece stay zero
     __syncthreads();
     if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
-    // window taps of this lane: s_win[lane + 32 n2].  The interior kernel reads them from shared memory per frame (at 168
-    // registers per thread a register copy would be spilled to local memory anyway); the edge kernel keeps a copy.
-    const float* wlane = s_win + lane;
+    const float* wlane = SP::NEED_WIN ? s_win + lane : nullptr;      // window taps of this lane when they are not in TMEM
 
-    const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_slot0, s_slot1, s_pb, s_zero};
+    const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_slot0, s_slot1, s_pb, s_ov};
     const long long total_frames = (long long)a.n_clips * a.frames_per_clip;
 
     float run_max = -INFINITY;
@@ -214,7 +228,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
         team_bar(bar_id);                                            // both spectra are in place
         bin_phase<R, MODE, tc, TM>(S0, S1, tb, X, 1e-8f, u, taddr + TMEM_COL_W01);
         team_bar(bar_id);
-        float mx = a.seg_major ? gather_lanes<MODE>(X, acc, a.n_mels, u) : gather_phase<MODE>(X, tb, acc, a.n_mels, u);
+        float mx = a.seg_major ? gather_lanes<MODE>(X, tb, acc, a.n_mels, u) : gather_phase<MODE>(X, tb, acc, a.n_mels, u);
         if constexpr (MODE == MODE_MIC && !tc) {
             team_bar(bar_id);                                        // pieces consumed: X is the GCC exchange buffer now
             if (h == 0) {
@@ -277,15 +291,21 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
                 const long long start = (long long)t * a.hop - G::N / 2 + a.origin;
                 {
                     float wreg[R];
+                    if constexpr (TM) {
+                        tmem_ld16(taddr + TMEM_COL_WIN, wreg);
+                        tmem_ld16(taddr + TMEM_COL_WIN + 16, wreg + 16);
+                    } else {
 #pragma unroll
-                    for (int n2 = 0; n2 < R; ++n2) wreg[n2] = wlane[32 * n2];
+                        for (int n2 = 0; n2 < R; ++n2) wreg[n2] = wlane[32 * n2];
+                    }
                     float2 v[R];
                     if (a.layout == LAYOUT_PCM16_LC)
                         stage1_load_reflect_pcm16<R>(reinterpret_cast<const short*>(a.wav) + (long long)clip * 4 * a.n_samples,
                                                      a.n_samples, h, start, wreg, v, lane);
                     else
                         stage1_load_reflect<R>(src, 2 * h, 2 * h + 1, start, wreg, v, lane);
-                    stage1_fft_store<R>(v, tb, E, lane);
+                    if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
+                    else stage1_fft_store<R>(v, tb, E, lane);
                 }
                 __syncwarp();
                 stage2_forward<R>(E, E, lane);
@@ -323,10 +343,15 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
                 stage1_load_raw<R, LAYOUT>(src, 2 * h, 2 * h + 1, start, raw, lane);
             }
         };
+        // FOA at n_fft = 1024 runs four warps per scheduler at 128 registers: the 2R prefetch registers do not fit, the loads
+        // are issued at the top of the frame instead and the other warps cover their latency (requesting them after the bin
+        // phase spills 376 B and measured 12.3 ms instead of 9.2)
+        constexpr bool PREFETCH = !(R == 32 && MODE == MODE_FOA);
         long long g = frame_index(sc, fi);
-        if (g >= 0) request(g);
+        if (PREFETCH && g >= 0) request(g);
 #pragma unroll 1
         while (g >= 0) {
+            if (!PREFETCH) request(g);
             float2 v[R];
             if constexpr (TM) {
                 float w[R];
@@ -342,7 +367,7 @@ __global__ void __launch_bounds__(max_warps<R>() * 32, 1) extract_kernel(Extract
             float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
             if (++fi == a.fpw || team * a.fpw + fi >= a.fsc) { fi = 0; sc += sc_step; }
             const long long g_next = frame_index(sc, fi);
-            if (g_next >= 0) request(g_next);
+            if (PREFETCH && g_next >= 0) request(g_next);
             if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
             else stage1_fft_store<R>(v, tb, E, lane);
             __syncwarp();
@@ -368,8 +393,20 @@ template <int R, int MODE, int LAYOUT, bool EDGE, bool TC>
 static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream) {
     a.frames_per_clip = EDGE ? a.t_lo + (a.t_tot - a.t_hi) : a.t_hi - a.t_lo;
     if (a.frames_per_clip <= 0) return SELD_OK;
+    // shared-memory geometry of this kernel variant: as many frame teams as fit, at most max_warps / 2
+    using SP = SmemPlan<R, MODE, TC>;
+    a.x_bytes = SP::x_bytes(plan->n_slots);
+    const int tb = SP::table_bytes(plan->n_mels);
+    const int wb = SP::team_bytes(plan->n_mels, a.x_bytes);
+    int teams = (plan->max_smem_optin - tb) / wb;
+    if (teams > max_warps<R, MODE>() / 2) teams = max_warps<R, MODE>() / 2;
+    if (const char* e = getenv("SELD_WARPS")) {           // experiments only: fewer warps per CTA
+        const int n = atoi(e) / 2;
+        if (n >= 1 && n < teams) teams = n;
+    }
+    if (teams < 1) { set_error("n_mels too large for the shared-memory budget"); return SELD_EUNSUPPORTED; }
     a.fpw = frames_per_team();
-    a.fsc = (plan->warps_per_cta / 2) * a.fpw;
+    a.fsc = teams * a.fpw;
     const long long per_super = a.fsc;
     a.n_super = ((long long)a.n_clips * a.frames_per_clip + per_super - 1) / per_super;
     long long grid = a.n_super < plan->grid ? a.n_super : plan->grid;
@@ -380,7 +417,7 @@ static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream)
                                            plan->max_smem_optin));
         configured.fetch_or(bit, std::memory_order_release);
     }
-    extract_kernel<R, MODE, LAYOUT, EDGE, TC><<<(int)grid, plan->warps_per_cta * 32, plan->extract_smem_bytes, stream>>>(a);
+    extract_kernel<R, MODE, LAYOUT, EDGE, TC><<<(int)grid, teams * 64, tb + teams * wb, stream>>>(a);
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;
 }
@@ -419,31 +456,6 @@ static int launch_mode(const seld_plan* plan, const ExtractArgs& a, cudaStream_t
 template <int R>
 static int launch_extract(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
     return plan->mode == SELD_MODE_FOA ? launch_mode<R, MODE_FOA>(plan, a, stream) : launch_mode<R, MODE_MIC>(plan, a, stream);
-}
-
-template <int R, int MODE>
-static void plan_geometry_mode(seld_plan* plan) {
-    using G = Geo<R>;
-    const int pstride = PieceGeo<MODE>::PSTRIDE * 8;
-    int e_bytes = align16(G::E_ELEMS * 8);
-    if (plan->n_slots * pstride > e_bytes) e_bytes = align16(plan->n_slots * pstride);
-    plan->e_bytes = e_bytes;
-    const int tb = table_bytes<R, MODE>(plan->n_mels);
-    const int wb = team_bytes<R, MODE>(plan->n_mels, e_bytes);
-    int warps = 2 * ((plan->max_smem_optin - tb) / wb);          // two warps per frame team
-    if (warps > max_warps<R>()) warps = max_warps<R>();
-    if (const char* e = getenv("SELD_WARPS")) {           // experiments only: fewer warps per CTA
-        const int n = atoi(e);
-        if (n >= 2 && n < warps) warps = n & ~1;
-    }
-    plan->warps_per_cta = warps;
-    plan->extract_smem_bytes = tb + (warps / 2) * wb;
-    plan->grid = plan->num_sms;
-}
-template <int R>
-static void plan_geometry(seld_plan* plan) {
-    if (plan->mode == SELD_MODE_FOA) plan_geometry_mode<R, MODE_FOA>(plan);
-    else plan_geometry_mode<R, MODE_MIC>(plan);
 }
 
 }  // namespace seld
@@ -548,6 +560,7 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
     up((void**)&plan->endmask, mp.endmask.data(), sizeof(unsigned long long) * mp.endmask.size());
     up((void**)&plan->slot0, mp.slot0.data(), sizeof(int) * mp.slot0.size());
     up((void**)&plan->slot1, mp.slot1.data(), sizeof(int) * mp.slot1.size());
+    up((void**)&plan->ov, mp.ov.data(), sizeof(int) * mp.ov.size());
     up((void**)&plan->pb, mp.pb.data(), sizeof(int) * mp.pb.size());
     if (e != cudaSuccess) {
         seld_plan_destroy(plan);
@@ -580,17 +593,17 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
         seld_plan_destroy(plan);
         return cuda_fail(e, "gcc basis upload");
     }
-    switch (n_fft) {
-        case 256: plan_geometry<8>(plan); break;
-        case 512: plan_geometry<16>(plan); break;
-        case 1024: plan_geometry<32>(plan); break;
-        default: plan_geometry<64>(plan); break;
+    // every kernel variant needs room for at least one frame team (checked again, per variant, at launch)
+    {
+        const int n_ch = (mode == SELD_MODE_FOA) ? 7 : 10;
+        const long long need = 3ll * (n_fft + 64) * 8 + (long long)plan->n_slots * 56 + (long long)n_mels * n_ch * 4 + 5ll * n_fft * 4 + 8192;
+        if (need > plan->max_smem_optin) {
+            seld_plan_destroy(plan);
+            set_error("n_mels too large for the shared-memory budget");
+            return SELD_EUNSUPPORTED;
+        }
     }
-    if (plan->warps_per_cta < 1) {
-        seld_plan_destroy(plan);
-        set_error("n_mels too large for the shared-memory budget");
-        return SELD_EUNSUPPORTED;
-    }
+    plan->grid = plan->num_sms;
     plan->stats_blocks = plan->num_sms * 4;
     *plan_out = plan;
     return SELD_OK;
@@ -605,6 +618,7 @@ int seld_plan_destroy(seld_plan_t plan) {
     cudaFree(plan->endmask);
     cudaFree(plan->slot0);
     cudaFree(plan->slot1);
+    cudaFree(plan->ov);
     cudaFree(plan->pb);
     cudaFree(plan->gcc_bt);
     delete plan;
@@ -661,8 +675,8 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
     a.endmask = plan->endmask;
     a.slot0 = plan->slot0;
     a.slot1 = plan->slot1;
+    a.ov = plan->ov;
     a.pb = plan->pb;
-    a.e_bytes = plan->e_bytes;
     a.t_g = a.t_raw < t_out ? a.t_raw : t_out;
     {
         const int64_t need = workspace_bytes_for(plan, n_clips, n_samples, t_out, centered);

@@ -47,7 +47,7 @@ struct Tables {             // CTA-shared constant tables (shared memory on the 
     const int* slot0;           // [TL]     record slot of lane u's first piece
     const int* slot1;           // [TL]     slot of its second piece (later pieces follow at +1); layouts: mel_pieces.h
     const int* pb;              // [n_mels + 2] compact layout: pieces with seg == m are [pb[m+1], pb[m+2])
-    const float2* zero_rec;     // [8] zeros: a piece record that contributes nothing
+    const int* ov;              // [64] segment-major layout: overflow slots of the 3rd / 4th piece of a segment
 };
 
 struct ClipSrc {            // one clip's samples: channel c, sample i -> base[c * chan_stride + i * samp_stride]
@@ -603,31 +603,29 @@ SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_
     return mx;
 }
 
-// Fast gather over the segment-major record layout (mel_pieces.h): team lane u totals slots u + 65 j, j < 4, with packed
-// adds -- consecutive lanes read consecutive records (no bank conflicts) and absent pieces are slots that were zeroed once
-// and never written.  mel[u] = A[u].x + A[u-1].y takes one shuffle per channel from the lane below; lane 0 of the team's
-// second warp re-totals segment 31 itself (same additions in the same order, so the CPU emulation, which always
-// re-totals, is bit-identical).
+// Fast gather over the segment-major record layout (mel_pieces.h): team lane u totals slots u, u + 65 and the two overflow
+// slots ov[u] names (the zero slot for all but the widest filters) with packed adds -- consecutive lanes read consecutive
+// records (no bank conflicts) and absent pieces are slots that were zeroed once and never written.  mel[u] = A[u].x +
+// A[u-1].y takes one shuffle per channel from the lane below; lane 0 of the team's second warp re-totals segment 31
+// itself (same additions in the same order, so the CPU emulation, which always re-totals, is bit-identical).
 template <int MODE>
-SELD_HD void seg_total(const float2* P, int seg, float2* A) {
+SELD_HD void seg_total(const float2* P, const Tables& tb, int seg, float2* A) {
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
     const float2* rec = P + seg * PSTRIDE;
+    const int ov = tb.ov[seg];
+    const float2* r2 = P + (ov & 0xffff) * PSTRIDE;
+    const float2* r3 = P + (ov >> 16) * PSTRIDE;
 #pragma unroll
-    for (int c = 0; c < NV; ++c) A[c] = rec[c];
-#pragma unroll
-    for (int j = 1; j < kSegMajorRanks; ++j) {
-#pragma unroll
-        for (int c = 0; c < NV; ++c) A[c] = padd(A[c], rec[j * kSegMajorPitch * PSTRIDE + c]);
-    }
+    for (int c = 0; c < NV; ++c) A[c] = padd(padd(padd(rec[c], rec[kSegMajorPitch * PSTRIDE + c]), r2[c]), r3[c]);
 }
 
 template <int MODE>
-SELD_HD float gather_lanes(const float2* P, float* acc, int n_mels, int u) {
+SELD_HD float gather_lanes(const float2* P, const Tables& tb, float* acc, int n_mels, int u) {
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
     float2 A[NV];
-    seg_total<MODE>(P, u, A);
+    seg_total<MODE>(P, tb, u, A);
     float below[NV];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -638,7 +636,7 @@ SELD_HD float gather_lanes(const float2* P, float* acc, int n_mels, int u) {
     }
     if (u == 32) {                                         // only the team's second warp takes this path
         float2 B[NV];
-        seg_total<MODE>(P, 31, B);
+        seg_total<MODE>(P, tb, 31, B);
 #pragma unroll
         for (int c = 0; c < NV; ++c) below[c] = B[c].y;
     }
@@ -646,7 +644,7 @@ SELD_HD float gather_lanes(const float2* P, float* acc, int n_mels, int u) {
     for (int c = 0; c < NV; ++c) below[c] = 0.f;
     if (u > 0) {
         float2 B[NV];
-        seg_total<MODE>(P, u - 1, B);
+        seg_total<MODE>(P, tb, u - 1, B);
         for (int c = 0; c < NV; ++c) below[c] = B[c].y;
     }
 #endif

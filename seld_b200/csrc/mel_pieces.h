@@ -22,15 +22,19 @@ struct MelPieces {
     int n_pieces = 0;
     int max_pieces_per_seg = 0;
     // Record layout.  compact: slot = piece index (pieces sorted by segment; the gather walks pb[]).
-    // seg_major (n_mels <= 64, <= kSegMajorRanks pieces per segment, no empty segment inside a lane's run): the j-th
-    // piece of segment s sits at slot s + kSegMajorPitch * j, so gather lane u reads slots u + kSegMajorPitch * j --
-    // consecutive lanes hit consecutive records (bank-conflict free) and absent pieces are slots that stay zero.
+    // seg_major (n_mels <= 64, <= kSegMajorRanks pieces per segment, no empty segment inside a lane's run): the first two
+    // pieces of segment s sit at slots s and s + kSegMajorPitch, so gather lane u reads slots u and u + 65 -- consecutive
+    // lanes hit consecutive records (bank-conflict free).  The few segments with a third / fourth piece (the widest
+    // filters) put them in an overflow area behind slot 130 and name them in ov[s] (low / high 16 bits); every other
+    // entry of ov points at slot kSegMajorZero, which is never written and therefore stays zero.
     bool seg_major = false;
     int n_slots = 0;
+    std::vector<int> ov;                          // [64]
 };
 
 constexpr int kSegMajorRanks = 4;
-constexpr int kSegMajorPitch = 65;      // odd, so the <= 4 pieces of one segment land in different bank groups
+constexpr int kSegMajorPitch = 65;      // odd, so the pieces of one segment land in different bank groups
+constexpr int kSegMajorZero = 64 + kSegMajorPitch;      // slot 129 = rank 1 of the non-existent segment 64
 
 // returns "" on success, else an error message
 inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, MelPieces& out) {
@@ -95,6 +99,22 @@ inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, Mel
     for (int l = 0; l < TL && out.seg_major; ++l)
         for (int p = first_piece[l] + 1; p < first_piece[l + 1]; ++p)
             if (piece_seg[p] != piece_seg[p - 1] + 1) out.seg_major = false;          // an empty segment inside the run
+    // slot of every piece in the segment-major layout
+    std::vector<int> slot_of(piece_seg.size(), 0);
+    out.ov.assign(64, kSegMajorZero | (kSegMajorZero << 16));
+    int n_over = 0;
+    for (size_t p = 0; p < piece_seg.size() && out.seg_major; ++p) {
+        int rank = 0;
+        while (int(p) - rank - 1 >= 0 && piece_seg[p - rank - 1] == piece_seg[p]) ++rank;
+        const int s = piece_seg[p];
+        if (rank < 2) {
+            slot_of[p] = s + kSegMajorPitch * rank;
+        } else {
+            slot_of[p] = 2 * kSegMajorPitch + n_over++;
+            if (rank == 2) out.ov[s] = (out.ov[s] & ~0xffff) | slot_of[p];
+            else out.ov[s] = (out.ov[s] & 0xffff) | (slot_of[p] << 16);
+        }
+    }
     for (int l = 0; l < TL; ++l) {
         const int p = first_piece[l];
         if (!out.seg_major || p >= first_piece[l + 1]) {
@@ -102,12 +122,10 @@ inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, Mel
             out.slot1[l] = out.slot0[l] + 1;
             continue;
         }
-        int rank = 0;
-        while (p - rank - 1 >= 0 && piece_seg[p - rank - 1] == piece_seg[p]) ++rank;
-        out.slot0[l] = piece_seg[p] + kSegMajorPitch * rank;
-        out.slot1[l] = piece_seg[p] + 1;
+        out.slot0[l] = slot_of[p];
+        out.slot1[l] = piece_seg[p] + 1;                      // later pieces of the lane open their segment: rank 0
     }
-    out.n_slots = out.seg_major ? 64 + kSegMajorPitch * (kSegMajorRanks - 1) : out.n_pieces;
+    out.n_slots = out.seg_major ? 2 * kSegMajorPitch + n_over : out.n_pieces;
     return "";
 }
 

@@ -23,16 +23,14 @@ struct seld_plan {
     unsigned long long* endmask;  // [64]
     int* slot0;      // [64]  record slot of each team lane's first / second piece (mel_pieces.h)
     int* slot1;      // [64]
+    int* ov;         // [64]  overflow slots of the segment-major record layout
     int* pb;         // [n_mels + 2]
     void* gcc_bt;    // MIC, n_fft 1024, 64 lags: fp16 [64][1024] basis of the tensor-core lag projection (else null)
     int n_pieces;
     int n_slots;     // piece records per frame in the layout in use
     int seg_major;   // segment-major record layout (fast gather) instead of the compact one
     int max_pieces_per_seg;
-    int e_bytes;     // per-team piece / GCC exchange buffer bytes
-    // extract launch geometry
-    int warps_per_cta;
-    int extract_smem_bytes;
+    // extract launch geometry (warps and shared memory are chosen per kernel variant at launch, extract.cu)
     int grid;
     // stats launch geometry
     int stats_blocks;

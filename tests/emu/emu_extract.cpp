@@ -47,7 +47,7 @@ static void run(const float* wav, int n_clips, long long L, int hop, int n_mels,
             stage2_inplace(EB);
             for (int u = 0; u < G::TL; ++u) bin_phase<R, MODE>(EA.data(), EB.data(), tb, X.data(), 1e-8f, u);
             for (int u = 0; u < G::TL; ++u)
-                cmax = fmaxf(cmax, fast_gather ? gather_lanes<MODE>(X.data(), acc.data(), n_mels, u)
+                cmax = fmaxf(cmax, fast_gather ? gather_lanes<MODE>(X.data(), tb, acc.data(), n_mels, u)
                                                : gather_phase<MODE>(X.data(), tb, acc.data(), n_mels, u));
             if (MODE == MODE_MIC) {
                 for (int l = 0; l < 32; ++l) gcc_stage1<R, 0>(EA.data(), EB.data(), X.data(), l);
@@ -74,9 +74,8 @@ extern "C" int emu_extract(const float* wav, int layout, int n_clips, long long 
         for (int l = 0; l < 32; ++l) tw_t[k2 * 32 + l] = lin[(l * k2) % n_fft];
     MelPieces mp;
     if (!build_mel_pieces(mel_fb, n_fft / 2 + 1, n_mels, mp).empty()) return -2;
-    static const float2 zero_rec[8] = {};
     Tables tb{window, tw_t.data(), lin, reinterpret_cast<const float2*>(mp.w01.data()), mp.endmask.data(), mp.slot0.data(), mp.slot1.data(),
-              mp.pb.data(), zero_rec};
+              mp.pb.data(), mp.ov.data()};
 #define GO3(RR, MM, LL) run<RR, MM, LL>(wav, n_clips, L, hop, n_mels, tb, mp.seg_major, T_out, out, clip_max)
 #define GO(RR)                                                                   \
     if (n_fft == 32 * RR) {                                                      \
