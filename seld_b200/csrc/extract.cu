@@ -344,8 +344,9 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
             }
         };
         // FOA at n_fft = 1024 runs four warps per scheduler at 128 registers: the 2R prefetch registers do not fit, the loads
-        // are issued at the top of the frame instead and the other warps cover their latency (requesting them after the bin
-        // phase spills 376 B and measured 12.3 ms instead of 9.2)
+        // are issued at the top of the frame instead and the other warps cover their latency.  Measured alternatives: requesting
+        // them after the bin phase spills 376 B (12.3 ms instead of 9.2); staging them through tensor memory four taps per
+        // bin step (tcgen05.st, then four tcgen05.ld at the next frame) couples the load latency into the team barriers (10.5 ms)
         constexpr bool PREFETCH = !(R == 32 && MODE == MODE_FOA);
         long long g = frame_index(sc, fi);
         if (PREFETCH && g >= 0) request(g);
