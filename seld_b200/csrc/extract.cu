@@ -76,10 +76,12 @@ struct ExtractArgs {
     long long n_super;        // super-chunks of fsc frames
 };
 
-static int frames_per_team() {   // consecutive frames a team handles per super-chunk (SELD_FPW overrides, for experiments)
+static int frames_per_team(int dflt) {   // consecutive frames a team handles per super-chunk (SELD_FPW overrides, for experiments)
     const char* e = getenv("SELD_FPW");
     const int n = e ? atoi(e) : 0;
-    return n > 0 ? n : 2;      // measured (600 planar FOA clips): 1 -> 11.59 ms, 2 -> 11.19, 3 -> 11.19, 4 -> 11.25, 8 -> 11.26
+    // measured (600 planar FOA clips, 16 warps, shared taps kept in tensor memory): 1 -> 9.72 ms, 2 -> 9.27, 4 -> 9.13, 8 -> 9.10;
+    // interleaved 9.82 / 9.52 / 9.22 / 9.15.  Kernels without the tap reuse are flat from 2 upwards.
+    return n > 0 ? n : dflt;
 }
 
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
@@ -351,8 +353,56 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         long long g = frame_index(sc, fi);
         if (PREFETCH && g >= 0) request(g);
 #pragma unroll 1
+        // Consecutive frames share R - 15 taps per lane (hop 480 = 15 * 32 samples: tap n2 of frame t + 1 is tap n2 + 15 of
+        // frame t).  The 16-warp kernel parks those 17 taps in its own tensor-memory columns and fetches only the 15 new
+        // ones from global memory for the following frame: half the global-load wavefronts, half the L2 requests.
+        constexpr int SH = 15;
+        constexpr bool KEEP = !PREFETCH && TM && R == 32;
+        const bool keep_ok = KEEP && a.hop == SH * 32;
+        const unsigned tkeep = taddr + TMEM_COL_KEEP + 64 * (warp >> 2);
+        int prev_clip = -1, prev_t = -2;
         while (g >= 0) {
-            if (!PREFETCH) request(g);
+            if constexpr (!PREFETCH) {
+                if constexpr (KEEP) {
+                    clip = int(g / a.frames_per_clip);
+                    t = a.t_lo + int(g - (long long)clip * a.frames_per_clip);
+                    start = (long long)t * a.hop - G::N / 2 + a.origin;
+                    if (keep_ok && clip == prev_clip && t == prev_t + 1) {
+                        float* rf = reinterpret_cast<float*>(raw);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tmem_ld16(tkeep, rf);
+                        tmem_ld16(tkeep + 16, rf + 16);
+                        tmem_ld2(tkeep + 32, rf[32], rf[33]);                     // taps 0 .. 16
+                        if constexpr (LAYOUT == LAYOUT_PCM16_LC) {
+                            const float* p = reinterpret_cast<const float*>(reinterpret_cast<const short*>(a.wav) +
+                                                                            ((long long)clip * a.n_samples + start + lane) * 4 + 2 * h);
+#pragma unroll
+                            for (int n2 = R - SH; n2 < R; ++n2) raw[n2].x = p[64 * n2];
+                        } else if constexpr (LAYOUT == LAYOUT_INTERLEAVED_LC) {
+                            const float2* p = reinterpret_cast<const float2*>(a.wav + ((long long)clip * a.n_samples + start + lane) * 4 + 2 * h);
+#pragma unroll
+                            for (int n2 = R - SH; n2 < R; ++n2) raw[n2] = p[64 * n2];
+                        } else {
+                            const float* pa = a.wav + ((long long)clip * 4 + 2 * h) * a.n_samples + start + lane;
+                            const float* pb = pa + a.n_samples;
+#pragma unroll
+                            for (int n2 = R - SH; n2 < R; ++n2) raw[n2] = make_float2(pa[32 * n2], pb[32 * n2]);
+                        }
+                    } else {
+                        request(g);
+                    }
+                    if (keep_ok) {                                                // taps 15 .. 31 are taps 0 .. 16 of the next frame
+                        const float* rf = reinterpret_cast<const float*>(raw);
+                        tmem_st16(tkeep, rf + 2 * SH);
+                        tmem_st16(tkeep + 16, rf + 2 * SH + 16);
+                        tmem_st2(tkeep + 32, rf[2 * SH + 32], rf[2 * SH + 33]);
+                    }
+                    prev_clip = clip;
+                    prev_t = t;
+                } else {
+                    request(g);
+                }
+            }
             float2 v[R];
             if constexpr (TM) {
                 float w[R];
@@ -406,7 +456,7 @@ static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream)
         if (n >= 1 && n < teams) teams = n;
     }
     if (teams < 1) { set_error("n_mels too large for the shared-memory budget"); return SELD_EUNSUPPORTED; }
-    a.fpw = frames_per_team();
+    a.fpw = frames_per_team((R == 32 && MODE == MODE_FOA && !EDGE) ? 8 : 2);
     a.fsc = teams * a.fpw;
     const long long per_super = a.fsc;
     a.n_super = ((long long)a.n_clips * a.frames_per_clip + per_super - 1) / per_super;

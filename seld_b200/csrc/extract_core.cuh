@@ -282,7 +282,8 @@ SELD_HD void stage1_fft_store(float2* v, const Tables& tb, float2* E, int lane) 
 // k2 < 32; [96, 114) mel weights (w0, w1) of team lane u's 9 bins.  Quadrants 0/2 hold the tables of a team's first
 // warp, 1/3 those of its second (warp parity == quadrant parity).
 #if defined(__CUDACC__)
-constexpr int TMEM_COL_WIN = 0, TMEM_COL_TW = 32, TMEM_COL_W01 = 96, TMEM_COLS = 128;
+constexpr int TMEM_COL_WIN = 0, TMEM_COL_TW = 32, TMEM_COL_W01 = 96, TMEM_COL_KEEP = 128, TMEM_COLS = 512;
+// [128, 384): per warp (four warps share a lane quadrant, 64 columns each) the samples two consecutive frames have in common
 
 __device__ __forceinline__ void tmem_ld2(unsigned taddr, float& a, float& b) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\ttcgen05.wait::ld.sync.aligned;"
@@ -294,6 +295,9 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float* r) {
                  : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
                    "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
                  : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(unsigned taddr, float a, float b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" :: "r"(taddr), "f"(a), "f"(b) : "memory");
 }
 __device__ __forceinline__ void tmem_st16(unsigned taddr, const float* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
