@@ -13,15 +13,20 @@ mode = sys.argv[1] if len(sys.argv) > 1 else 'foa'
 base = [make_clip(1000 + i, device='cuda') for i in range(8)]
 for clips in (74, 148, 296, 600):
     wav = torch.stack([base[i % 8] for i in range(clips)])
-    for layout in ('planar', 'interleaved'):
-        w = wav if layout == 'planar' else wav.transpose(1, 2).contiguous()
+    for layout in ('planar', 'interleaved', 'pcm16'):
+        if layout == 'planar':
+            w = wav
+        elif layout == 'interleaved':
+            w = wav.transpose(1, 2).contiguous()
+        else:                                   # 16-bit PCM in WAV frame order, decoded by the kernel
+            w = (wav.transpose(1, 2) * 32767.0).round().clamp(-32768, 32767).to(torch.int16).contiguous()
         out = torch.empty(clips, 3000, 64, 7 if mode == 'foa' else 10, device='cuda')
         for _ in range(2):
-            pipeline.extract_batch(w, 24000, mode=mode, t_out=3000, layout=layout, out=out, **kw)
+            pipeline.extract_batch(w, 24000, mode=mode, t_out=3000, layout='interleaved' if layout == 'pcm16' else layout, out=out, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(3):
-            pipeline.extract_batch(w, 24000, mode=mode, t_out=3000, layout=layout, out=out, **kw)
+            pipeline.extract_batch(w, 24000, mode=mode, t_out=3000, layout='interleaved' if layout == 'pcm16' else layout, out=out, **kw)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
