@@ -228,3 +228,20 @@ def test_other_mel_counts_against_oracle(mode, n_mels):
         e_got = np.abs(got[..., :4] - truth[..., :4]).max()
         assert e_got <= 3e-4, e_got
         assert np.abs(got[..., 4:] - ref[..., 4:]).max() <= 1e-3
+
+
+@pytest.mark.parametrize('n_samples', [513, 700, 1024, 1503, 1504, 1984, 2500])
+def test_very_short_clips_against_oracle(n_samples):
+    """Clips of one to a few frames at the production geometry: every frame needs reflection (no interior launch at all
+    below 1 504 samples), the frame count is 1 + L // hop, and a batch mixes nothing up."""
+    from oracle import extractor as O
+    from seld_b200 import pipeline
+    from seld_b200.synth import make_clips
+    wav = make_clips([5, 6, 7], n_samples)
+    for mode in ('foa', 'mic'):
+        feat, key = pipeline.extract_batch(wav.cuda(), 24000, mode=mode, **PROD)
+        assert feat.shape[1] == 1 + n_samples // 480
+        pipeline.finalize_(feat, key, feat.shape[1])
+        for i in range(3):
+            ref = O.extract_features_port(wav[i], 24000, mode=mode, **PROD)
+            check_features(feat[i].cpu().numpy(), ref, mode, f'{mode} L={n_samples} clip {i}')
