@@ -245,3 +245,27 @@ def test_very_short_clips_against_oracle(n_samples):
         for i in range(3):
             ref = O.extract_features_port(wav[i], 24000, mode=mode, **PROD)
             check_features(feat[i].cpu().numpy(), ref, mode, f'{mode} L={n_samples} clip {i}')
+
+
+@pytest.mark.parametrize('use_tc', [True, False])
+def test_mic_with_a_silent_channel(use_tc):
+    """A dead microphone (one all-zero channel).  The pairs that do not involve it must match the reference as usual.
+    For the three pairs that do, the reference's own output is an artefact -- its cross-spectrum is an exact signed zero and
+    torch.angle(+-0 +- 0i) is 0 or pi depending on the sign bits -- while this kernel, which packs two real channels per
+    complex FFT, sees float32 rounding leakage of the partner channel in the dead one and returns unit phasors of that
+    noise.  Neither carries information; the documented behaviour is: finite, |value| <= 1, everything
+    else unaffected."""
+    from oracle import extractor as O
+    from seld_b200 import pipeline
+    from seld_b200.synth import make_clips
+    wav = make_clips([21], 24000)
+    wav[0, 2] = 0.0                                                        # microphone 2 is dead
+    feat, key = pipeline.extract_batch(wav.cuda(), 24000, mode='mic', use_tensor_cores=use_tc, **PROD)
+    pipeline.finalize_(feat, key, feat.shape[1])
+    got = feat[0].cpu().numpy()
+    ref = O.extract_features_port(wav[0], 24000, mode='mic', **PROD)
+    assert np.abs(got[..., :4] - ref[..., :4]).max() <= 1e-4               # log-mel, dead channel included (-100 dB floor / clamp)
+    live = [4 + p for p in (0, 2, 4)]                                       # pairs (0,1), (0,3), (1,3)
+    dead = [4 + p for p in (1, 3, 5)]                                       # pairs (0,2), (1,2), (2,3)
+    assert np.abs(got[..., live] - ref[..., live]).max() <= 1e-3
+    assert np.isfinite(got[..., dead]).all() and np.abs(got[..., dead]).max() <= 1.0 + 1e-3
