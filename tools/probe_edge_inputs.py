@@ -22,3 +22,10 @@ run('loud x1e4', base*1e4); run('quiet x1e-6', base*1e-6); run('quiet x1e-3', ba
 run('dc 0.5', torch.full((1,4,24000), 0.5))
 w = base.clone(); w[0,:, :12000] = 0; run('half silent', w)
 w = torch.zeros(1,4,24000); w[0,:,10000] = 1.0; run('impulse', w)
+# CUDA-core GCC path on the quiet noise-free case (per-channel unit phasors rescale, no |R|^2 window)
+for scale in (1e-3, 1e-6):
+    w = base * scale
+    feat, key = pipeline.extract_batch(w.cuda(), 24000, mode='mic', use_tensor_cores=False, **PROD)
+    pipeline.finalize_(feat, key, feat.shape[1])
+    ref = O.extract_features_port(w[0], 24000, mode='mic', **PROD)
+    print('quiet x%g mic CUDA-core path: gcc err %.2e' % (scale, np.abs(feat[0].cpu().numpy()[..., 4:] - ref[..., 4:]).max()), flush=True)
