@@ -453,17 +453,11 @@ SELD_HD float2 pair_phasor(float2 um, float2 un) {   // exp(i angle(conj(Xm) Xn)
     return make_float2(um.x * un.x + um.y * un.y, um.x * un.y - um.y * un.x);
 }
 
-// exp(i angle(conj(a) b)) = R / |R| with R = conj(a) b, and 1 for R == 0 (angle(0) = 0), in packed arithmetic.
-// |R|^2 below the smallest normal float flushes to 0 -> 1 (spectra under ~3e-10 of full scale; never reached by 16-bit
-// audio, whose smallest non-zero bin is ~1e-5).
-SELD_HD float2 cross_phasor(float2 a, float2 b) {
-    const float2 t = pmul(make_float2(a.x, a.x), b);                              // (ax bx, ax by)
-    const float2 r = pfma(make_float2(a.y, -a.y), make_float2(b.y, b.x), t);      // (ax bx + ay by, ax by - ay bx)
-    const float2 q = pmul(r, r);
-    const float n2 = q.x + q.y;
-    const float inv = rsqrt_ftz(n2);
-    const float2 p = pmul(r, make_float2(inv, inv));
-    return (n2 >= 1.17549435e-38f) ? p : make_float2(1.f, 0.f);
+// conj(um) * un for unit phasors um, un (packed arithmetic); (1, 0) when either channel is zero: exp(i angle(0)) = 1
+SELD_HD float2 unit_pair(float2 um, float2 un, bool zero) {
+    const float2 t = pmul(make_float2(um.x, um.x), un);                            // (mx nx, mx ny)
+    const float2 r = pfma(make_float2(um.y, -um.y), make_float2(un.y, un.x), t);   // (mx nx + my ny, mx ny - my nx)
+    return zero ? make_float2(1.f, 0.f) : r;
 }
 
 SELD_HD float pack_half2(float lo, float hi) {          // two floats -> one 32-bit word of two fp16 (round to nearest)
@@ -477,7 +471,7 @@ SELD_HD float pack_half2(float lo, float hi) {          // two floats -> one 32-
 }
 
 // GCC_TC (MIC only): instead of per-channel unit phasors for the CUDA-core inverse transforms, write the six PAIR
-// phasors exp(i angle(conj(X_m) X_n)) as fp16 (re, im) words into the bin's own four spectrum slots -- the A operand
+// phasors exp(i angle(conj(X_m) X_n)) = conj(u_m) u_n as fp16 (re, im) words into the bin's own four spectrum slots -- the A operand
 // rows of the tensor-core lag projection (gcc_gemm.cu), copied out by gcc_tc_copy_out.
 template <int R, int MODE, bool GCC_TC = false, bool W_TMEM = false>
 SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, float eps, int u,      // u: team lane, 0..TL-1
@@ -524,8 +518,19 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
             val[6] = iz * inv4;
         } else {
             if (valid && GCC_TC) {
-                const float2 p01 = cross_phasor(ch[0], ch[1]), p02 = cross_phasor(ch[0], ch[2]), p03 = cross_phasor(ch[0], ch[3]);
-                const float2 p12 = cross_phasor(ch[1], ch[2]), p13 = cross_phasor(ch[1], ch[3]), p23 = cross_phasor(ch[2], ch[3]);
+                // per-channel unit phasors from the powers the log-mel block needs anyway (one MUFU.RSQ each; |X|^2 stays in
+                // range for any spectrum a float can hold), then six complex products; a pair with a zero channel is 1
+                float2 uc[4];
+                bool zc[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    zc[c] = !(val[c] >= 1.17549435e-38f);
+                    const float inv = rsqrt_ftz(val[c]);
+                    uc[c] = pmul(ch[c], make_float2(inv, inv));
+                }
+                const float2 p01 = unit_pair(uc[0], uc[1], zc[0] || zc[1]), p02 = unit_pair(uc[0], uc[2], zc[0] || zc[2]);
+                const float2 p03 = unit_pair(uc[0], uc[3], zc[0] || zc[3]), p12 = unit_pair(uc[1], uc[2], zc[1] || zc[2]);
+                const float2 p13 = unit_pair(uc[1], uc[3], zc[1] || zc[3]), p23 = unit_pair(uc[2], uc[3], zc[2] || zc[3]);
                 if (k == 0 || k == N / 2) {          // real bins: six real parts as three half2 words
                     S0[k] = make_float2(pack_half2(p01.x, p02.x), pack_half2(p03.x, p12.x));
                     S1[k] = make_float2(pack_half2(p13.x, p23.x), 0.f);
