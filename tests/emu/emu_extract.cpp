@@ -88,3 +88,16 @@ extern "C" int emu_extract(const float* wav, int layout, int n_clips, long long 
 }
 
 extern "C" float emu_key_roundtrip(float f) { return key_to_float(float_to_key(f)); }
+
+// Mel piece tables as seld_plan_create builds them (for tests/test_emu_cpu.py::test_mel_piece_layout_invariants).
+// info: [bpt, n_pieces, max_pieces_per_seg, seg_major, n_slots, zero_slot, pitch]
+extern "C" int emu_mel_layout(const float* mel_fb, int n_bins, int n_mels, int* info, int* slot0, int* slot1, int* ov,
+                              unsigned long long* endmask) {
+    MelPieces mp;
+    if (!build_mel_pieces(mel_fb, n_bins, n_mels, mp).empty()) return -2;
+    info[0] = mp.bpt; info[1] = mp.n_pieces; info[2] = mp.max_pieces_per_seg; info[3] = mp.seg_major ? 1 : 0;
+    info[4] = mp.n_slots; info[5] = kSegMajorZero; info[6] = kSegMajorPitch;
+    for (int l = 0; l < kTeamLanes; ++l) { slot0[l] = mp.slot0[l]; slot1[l] = mp.slot1[l]; endmask[l] = mp.endmask[l]; }
+    for (int s = 0; s < 64; ++s) ov[s] = mp.ov[s];
+    return 0;
+}

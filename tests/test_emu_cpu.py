@@ -78,3 +78,48 @@ def test_ordered_key_roundtrip(emu):
     emu.emu_key_roundtrip.argtypes = [ctypes.c_float]
     for v in (-100.0, -0.0, 0.0, 1e-30, 25.9, -1e30, float('inf'), float('-inf')):
         assert emu.emu_key_roundtrip(v) == np.float32(v)
+
+
+@pytest.mark.parametrize('n_fft,sr,n_mels', [(1024, 24000, 64), (1024, 48000, 64), (512, 16000, 64), (256, 8000, 32),
+                                               (2048, 48000, 64), (1024, 24000, 40), (1024, 24000, 128)])
+def test_mel_piece_layout_invariants(emu, n_fft, sr, n_mels):
+    """The record layout the bin phase writes and the gather reads (csrc/mel_pieces.h): every piece gets its own slot
+    below n_slots, the zero slot is never written, and in the segment-major layout the j-th piece of segment s is exactly
+    where the gather looks for it -- slot s, slot s + 65, then the two overflow slots ov[s] names."""
+    n_bins = n_fft // 2 + 1
+    fb = np.ascontiguousarray(tables.melscale_fbanks_htk(n_bins, sr, n_mels).numpy())
+    info = np.zeros(8, np.int32)
+    slot0, slot1, ov = np.zeros(64, np.int32), np.zeros(64, np.int32), np.zeros(64, np.int32)
+    endmask = np.zeros(64, np.uint64)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert emu.emu_mel_layout(p(fb), n_bins, n_mels, p(info), p(slot0), p(slot1), p(ov), p(endmask)) == 0
+    bpt, n_pieces, max_per_seg, seg_major, n_slots, zero_slot, pitch = (int(v) for v in info[:7])
+    assert bpt == -(-n_bins // 64) and 64 * bpt <= n_fft
+    seg_of_bin = [int(np.flatnonzero(fb[k])[0]) if fb[k].any() else -1 for k in range(n_bins)]
+    # walk every team lane the way bin_phase does
+    pieces = []                                     # (slot, seg) in write order
+    for u in range(64):
+        slot, nxt = int(slot0[u]), int(slot1[u])
+        for i in range(bpt):
+            if (int(endmask[u]) >> i) & 1:
+                k = u * bpt + i
+                assert k < n_bins and seg_of_bin[k] >= 0
+                pieces.append((slot, seg_of_bin[k]))
+                slot, nxt = nxt, nxt + 1
+    assert len(pieces) == n_pieces
+    slots = [s for s, _ in pieces]
+    assert len(set(slots)) == n_pieces and max(slots) < n_slots and min(slots) >= 0
+    assert not seg_major or (n_mels <= 64 and max_per_seg <= 4)
+    assert seg_major or n_mels > 64 or max_per_seg > 4 or n_fft != 1024      # the production bank must take the fast layout
+    if seg_major:
+        assert zero_slot not in slots and zero_slot < n_slots
+        by_seg = {}
+        for s, seg in pieces:
+            by_seg.setdefault(seg, []).append(s)
+        for seg in range(64):
+            want = by_seg.get(seg, [])
+            reads = [seg, seg + pitch, int(ov[seg]) & 0xffff, int(ov[seg]) >> 16]
+            assert reads[:len(want)] == want, (seg, want, reads)                    # pieces in rank order where the gather reads
+            assert all(r == zero_slot or r not in slots for r in reads[len(want):])  # the rest are never-written slots
+    else:
+        assert slots == list(range(n_pieces))                                       # compact layout: piece index
