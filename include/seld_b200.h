@@ -87,16 +87,18 @@ SELD_API int64_t seld_plan_num_frames(seld_plan_t plan, int64_t n_samples);
  *                      clamp (it needs the clip-global maximum); rows >= 1 + n_samples/hop are zero
  *   clip_max_key_dev   [n_clips] uint32 order-preserving keys of the per-clip maximum dB over ALL frames
  *                      (including frames >= t_out, as the reference takes the max before truncating);
- *                      reset by this call; decode with seld_clip_max_decode
+ *                      reset by this call; decode with seld_clip_max_decode.  A NaN log-mel value makes the key NaN's
+ *                      (the reference's db.max() is NaN then, and with it the whole clip's log-mel block).
+ *   workspace_dev      unused (kept for ABI stability); workspace_bytes < 0 selects the CUDA-core GCC path for MIC
+ *                      plans that would otherwise use the fused tensor-core lag projection (n_fft 1024, 64 lags)
  */
 SELD_API int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips, int64_t n_samples, int t_out,
                  float* feat_raw_dev, uint32_t* clip_max_key_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
 
 /*
- * Scratch for the tensor-core GCC path (MIC plans with n_fft 1024 and 64 lags): the extractor writes one 2 KB row of
- * fp16 pair phasors per (frame, pair) into workspace_dev and the tcgen05 GEMM (see seld_gcc_gemm) projects them onto
- * the 64 lags.  Returns 0 when the plan has no such path.  With workspace_dev == NULL (or too small) seld_extract
- * falls back to the pruned inverse FFT on the CUDA cores -- same results within 1e-4, about 2x slower for MIC.
+ * Always 0 since the tensor-core GCC lag projection (reference feature_extractor.py:209-211) runs inside the extractor:
+ * basis resident in tensor memory, pair-phasor rows in shared memory, tcgen05.mma per frame -- no scratch in HBM.
+ * Kept so that round-1 callers still link.
  */
 SELD_API int64_t seld_extract_workspace_bytes(seld_plan_t plan, int n_clips, int64_t n_samples, int t_out);
 
@@ -115,8 +117,6 @@ SELD_API int seld_extract_pcm16(seld_plan_t plan, const int16_t* pcm_dev, int n_
  * starts at chunk sample t * hop (no centring, no reflection), so the rows equal rows s0/hop .. of the full-clip
  * extraction bit for bit.  n_samples >= n_fft; frames = 1 + (n_samples - n_fft) / hop.  chunk_max_key_dev receives the
  * chunk maxima; for the reference's clip-global top_db pass the cached clip maxima to seld_finalize instead.
- * (With a MIC workspace, size it with the chunk's frame count: n_chunks * frames * 6 rows of 2 KB, rounded up to
- * 21-frame tiles, plus frames * 1 KB.)
  */
 SELD_API int seld_extract_chunks(seld_plan_t plan, const float* wav_dev, int layout, int n_chunks, int64_t n_samples, int t_out,
                                  float* feat_raw_dev, uint32_t* chunk_max_key_dev, void* workspace_dev, int64_t workspace_bytes,

@@ -22,25 +22,32 @@
 
 namespace seld {
 
-struct GccGemmArgs {          // gcc_gemm.cu
-    const __half* A;
-    const __half* Bt;
-    long long n_tiles;
-    float scale;
-    float* dense_out;
-    long long dense_rows;
-    float* feat;
-    const float* logmel;
-    long long n_frames;
-    int frames_per_clip, t_out;
-};
-int launch_gcc_gemm(const GccGemmArgs& g, int num_sms, cudaStream_t st);
-
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 int cuda_fail(cudaError_t e, const char* what) {
     set_error(std::string(what) + ": " + cudaGetErrorString(e));
     return SELD_ECUDA;
+}
+
+int device_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::atomic<int>& c = cache[dev & 63];
+    int v = c.load(std::memory_order_acquire);
+    if (v == 0) {
+        v = 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        c.store(v, std::memory_order_release);
+    }
+    return v;
+}
+
+bool first_use_on_device(unsigned long long* slot_bits) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return !(__atomic_fetch_or(slot_bits, bit, __ATOMIC_ACQ_REL) & bit);
 }
 
 struct ExtractArgs {
@@ -65,10 +72,8 @@ struct ExtractArgs {
     int x_bytes;              // per-team piece / GCC exchange buffer size (SmemPlan::x_bytes)
     int seg_major;            // piece records in the segment-major layout: gather_lanes (else the compact layout + gather_phase)
     int x_zero_f2;            // float2 elements of the piece buffer that must read as zero where no piece is stored
-    int gcc_tc;               // MIC: write fp16 pair phasors to gcc_rows; the tensor-core GEMM does the lag projection
-    int t_g;                  // frames per clip that have a stored row (min(t_raw, t_out))
-    float* gcc_rows;          // tile-blocked fp16 pair phasors, A operand of gcc_gemm (21 frames = 126 rows per tile)
-    float* gcc_logmel;        // [n_clips * t_g][n_mels][4] un-clamped log-mel; gcc_gemm assembles the complete rows
+    int gcc_tc;               // MIC, n_fft 1024, 64 lags: fused tensor-core lag projection (extract_core.cuh)
+    const void* gcc_basis;    // fp16 [64 lags][1024] basis of that projection (x512), row-major
     int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
     int origin;               // frame t starts at sample t*hop - n_fft/2 + origin (0: centred STFT; n_fft/2: uncentred chunks)
     int fpw;                  // consecutive frames per team per super-chunk
@@ -85,6 +90,8 @@ static int frames_per_team(int dflt) {   // consecutive frames a team handles pe
 }
 
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
+constexpr int kGccTileBytes = GT_BYTES;          // fused GCC: phasor tile (the exchange buffers alias it) ...
+constexpr int kGccNyqBytes = GT_NYQ_BYTES + 16;  // ... + the Nyquist column + the dead-channel flags of the two warps
 
 // Shared-memory plan of one kernel variant.  CTA-shared tables first, then one region per frame team (two warps): an
 // exchange buffer per warp (its spectrum overwrites it in place), the piece / GCC exchange buffer, the staged output row.
@@ -93,22 +100,26 @@ template <int R, int MODE, bool TC>
 struct SmemPlan {
     using G = Geo<R>;
     static constexpr bool TM = (R == 32);                               // per-lane constants in tensor memory
-    static constexpr bool tc = TC && MODE == MODE_MIC && R == 32;       // tensor-core GCC: this kernel only writes phasor rows
+    static constexpr bool tc = TC && MODE == MODE_MIC && R == 32;       // fused tensor-core GCC: the spectrum buffer doubles as the MMA's B tile
     static constexpr bool NEED_TW = !TM || (MODE == MODE_MIC && !tc);   // stage-1 twiddles (also the fast CUDA-core GCC stage 2)
     static constexpr bool NEED_W01 = !TM;
     static constexpr bool NEED_WIN = !TM;
     static constexpr bool NEED_TWLIN = (MODE == MODE_MIC && !tc);
     __host__ __device__ static constexpr int table_bytes(int n_mels) {
         return (NEED_TW ? align16(G::N * 8) : 0) + (NEED_W01 ? align16(G::TL * G::BPT * 8) : 0) + align16(G::TL * 8) + 2 * align16(G::TL * 4) +
-               align16((n_mels + 2) * 4) + align16(64 * 4) + 16 + (NEED_WIN ? align16(G::N * 4) : 0) + (NEED_TWLIN ? align16(G::N * 8) : 0);
+               align16((n_mels + 2) * 4) + align16(64 * 4) + 16 + (NEED_WIN ? align16(G::N * 4) : 0) + (NEED_TWLIN ? align16(G::N * 8) : 0) +
+               (tc ? 64 : 0);                                           // one mbarrier per frame team
     }
     __host__ __device__ static constexpr int x_bytes(int n_slots) {
         const int pieces = align16(n_slots * PieceGeo<MODE>::PSTRIDE * 8);
         const int exchange = (MODE == MODE_MIC && !tc) ? align16(G::E_ELEMS * 8) : 0;
         return pieces > exchange ? pieces : exchange;
     }
+    __host__ __device__ static constexpr int spec_bytes() {            // the two exchange / spectrum buffers of a team
+        return tc ? kGccTileBytes + kGccNyqBytes : 2 * align16(G::E_ELEMS * 8);
+    }
     __host__ __device__ static constexpr int team_bytes(int n_mels, int xb) {
-        return 2 * align16(G::E_ELEMS * 8) + xb + align16(n_mels * (MODE == MODE_FOA ? 7 : 10) * 4);
+        return spec_bytes() + xb + align16(n_mels * (MODE == MODE_FOA ? 7 : 10) * 4);
     }
 };
 
@@ -119,9 +130,14 @@ template <int R, int MODE>
 __host__ __device__ constexpr int max_warps() { return R <= 16 ? 16 : (R == 32 ? (MODE == MODE_FOA ? 16 : 12) : 4); }
 
 __device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
+__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory"); }
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 
 // EDGE = false: interior frames only, loads specialised on LAYOUT (the hot kernel).
 // EDGE = true : the few frames per clip that need reflection, plus the zero padding rows (generic strided loads).
+// TC (MIC, n_fft 1024, 64 lags): the GCC lag projection runs on the tensor cores inside this kernel (extract_core.cuh,
+// "fused tensor-core GCC").  Two neighbouring teams form a PAIR there: their four warps cover the four tensor-memory
+// subpartitions, which is what reading an M = 64 accumulator back takes, so the pair reads both teams' accumulators.
 template <int R, int MODE, int LAYOUT, bool EDGE, bool TC>
 __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(ExtractArgs a) {
     using G = Geo<R>;
@@ -138,6 +154,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     // ~18 % of the shared-memory wavefronts off the LSU data pipe this kernel is bound by (extract_core.cuh)
     using SP = SmemPlan<R, MODE, TC>;
     constexpr bool TM = SP::TM;
+    constexpr bool FUSED = SP::tc;
     // ---- CTA-shared tables
     unsigned char* p = smem;
     float2* s_tw_t = nullptr;
@@ -154,6 +171,8 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     if constexpr (SP::NEED_WIN) { s_win = reinterpret_cast<float*>(p);  p += align16(G::N * 4); }
     float2* s_tw_lin = nullptr;
     if constexpr (SP::NEED_TWLIN) { s_tw_lin = reinterpret_cast<float2*>(p);  p += align16(G::N * 8); }
+    unsigned long long* s_mbar = nullptr;                                    // fused GCC: "the MMAs of team t have completed"
+    if constexpr (FUSED) { s_mbar = reinterpret_cast<unsigned long long*>(p);  p += 64; }
     const float wscale = ((EDGE ? a.layout : LAYOUT) == LAYOUT_PCM16_LC) ? (1.0f / 32768.0f) : 1.0f;    // exact: folds the PCM decode
     for (int i = threadIdx.x; i < G::N; i += blockDim.x) {
         if constexpr (SP::NEED_WIN) s_win[i] = a.window[i] * wscale;
@@ -168,12 +187,18 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         s_slot1[threadIdx.x] = a.slot1[threadIdx.x];
         s_ov[threadIdx.x] = a.ov[threadIdx.x];
     }
+    if constexpr (FUSED) {
+        if (threadIdx.x < 8) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&s_mbar[threadIdx.x])));
+            asm volatile("fence.mbarrier_init.release.cluster;");
+        }
+    }
     unsigned taddr = 0;
     if constexpr (TM) {
         static_assert(!TM || 2 * G::BPT <= 32, "mel weights of a lane must fit 32 TMEM columns");
         if (warp == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                         :: "r"(static_cast<unsigned>(__cvta_generic_to_shared(&s_tmem_base))), "r"(TMEM_COLS));
+                         :: "r"(smem_addr(&s_tmem_base)), "r"(TMEM_COLS));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         }
         asm volatile("tcgen05.fence::before_thread_sync;");
@@ -201,19 +226,42 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                 for (int i = 0; i < 16; ++i) r[i] = (16 * c + i < 2 * G::BPT) ? w01[16 * c + i] : 0.f;
                 tmem_st16(taddr + TMEM_COL_W01 + 16 * c, r);
             }
+            if constexpr (FUSED) {
+                // the lag-projection basis, A operand of every MMA of this kernel: lane l of quadrant q holds lag row
+                // 16 q + (l & 15), K half (l >> 4), two fp16 per column -> 256 columns
+                const uint4* src = reinterpret_cast<const uint4*>(a.gcc_basis) + (size_t(16 * warp + (lane & 15)) * 1024 + size_t(lane >> 4) * 512) / 8;
+#pragma unroll 1
+                for (int g = 0; g < 16; ++g) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 q = __ldg(src + 4 * g + i);
+                        r[4 * i] = __uint_as_float(q.x); r[4 * i + 1] = __uint_as_float(q.y);
+                        r[4 * i + 2] = __uint_as_float(q.z); r[4 * i + 3] = __uint_as_float(q.w);
+                    }
+                    tmem_st16(taddr + TMEM_COL_BASIS + 16 * g, r);
+                }
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;");
     }
     // ---- per-team regions
-    unsigned char* tp = p + size_t(team) * SP::team_bytes(a.n_mels, a.x_bytes);
-    float2* S0 = reinterpret_cast<float2*>(tp);  tp += align16(G::E_ELEMS * 8);     // warp 0: exchange, then spectrum of pair 0
-    float2* S1 = reinterpret_cast<float2*>(tp);  tp += align16(G::E_ELEMS * 8);     // warp 1: exchange, then spectrum of pair 1
+    const int team_stride = SP::team_bytes(a.n_mels, a.x_bytes);
+    unsigned char* tp = p + size_t(team) * team_stride;
+    unsigned char* tile = tp;                                                        // fused GCC: spectrum / phasor tile + Nyquist column
+    unsigned char* nyq = tp + kGccTileBytes;
+    float2* S0 = reinterpret_cast<float2*>(tp);                                      // warp 0: exchange, then spectrum of pair 0
+    float2* S1 = reinterpret_cast<float2*>(tp + align16(G::E_ELEMS * 8));            // warp 1: exchange, then spectrum of pair 1
+    tp += SP::spec_bytes();
     float2* X = reinterpret_cast<float2*>(tp);  tp += a.x_bytes;                    // mel pieces, then GCC exchange
     float* acc = reinterpret_cast<float*>(tp);
     float2* E = h ? S1 : S0;
     const int row_elems = a.n_mels * C;
     for (int i = u; i < a.x_zero_f2; i += TL) X[i] = make_float2(0.f, 0.f);    // segment-major slots without a piece stay zero
+    if constexpr (FUSED) {
+        static_assert(!FUSED || 2 * align16(G::E_ELEMS * 8) <= kGccTileBytes, "the exchange buffers alias the phasor tile");
+        for (int i = u; i < kGccNyqBytes / 4; i += TL) reinterpret_cast<float*>(nyq)[i] = 0.f;
+    }
     __syncthreads();
     if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
     const float* wlane = SP::NEED_WIN ? s_win + lane : nullptr;      // window taps of this lane when they are not in TMEM
@@ -222,96 +270,167 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     const long long total_frames = (long long)a.n_clips * a.frames_per_clip;
 
     float run_max = -INFINITY;
+    bool run_nan = false;
     int run_clip = -1;
+    // fused GCC: partner team of the pair, its staged row, phase parities of the two teams' MMA barriers
+    const int pteam = team ^ 1;
+    float* acc_part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(acc) + (pteam - team) * team_stride);
+    unsigned par_mine = 0, par_part = 0;
+    volatile unsigned* dead_flags = reinterpret_cast<volatile unsigned*>(nyq + GT_NYQ_BYTES);     // [2]: bits (channel 2h, 2h + 1) of warp h
 
-    // everything after the team's two packed FFTs: mel pieces, gather, (GCC), row store, running clip maximum
-    auto finish_frame = [&](int clip, int t, float* row) {
-        constexpr bool tc = TC && MODE == MODE_MIC && R == 32;       // tensor-core GCC: this kernel only writes phasor rows
-        team_bar(bar_id);                                            // both spectra are in place
-        bin_phase<R, MODE, tc, TM>(S0, S1, tb, X, 1e-8f, u, taddr + TMEM_COL_W01);
-        team_bar(bar_id);
-        float mx = a.seg_major ? gather_lanes<MODE>(X, tb, acc, a.n_mels, u) : gather_phase<MODE>(X, tb, acc, a.n_mels, u);
-        if constexpr (MODE == MODE_MIC && !tc) {
-            team_bar(bar_id);                                        // pieces consumed: X is the GCC exchange buffer now
-            if (h == 0) {
-                gcc_stage1<R, 0>(S0, S1, X, lane);
-                __syncwarp();
-                gcc_stage2<R, 0>(X, tb, acc, a.n_mels, lane);
-                __syncwarp();
-                gcc_stage1<R, 1>(S0, S1, X, lane);
-                __syncwarp();
-                gcc_stage2<R, 1>(X, tb, acc, a.n_mels, lane);
-                __syncwarp();
-                gcc_stage1<R, 2>(S0, S1, X, lane);
-                __syncwarp();
-                gcc_stage2<R, 2>(X, tb, acc, a.n_mels, lane);
-                __syncwarp();
-                for (int i = lane; i < a.x_zero_f2; i += 32) X[i] = make_float2(0.f, 0.f);   // X goes back to being the piece buffer
-            }
+    // forward FFT stage 2 of this warp; the fused kernel lays the spectrum out as the MMA's B tile (both warps' rows
+    // interleave there, so every lane must hold its column before anyone stores)
+    auto stage2 = [&]() {
+        if constexpr (FUSED) {
+            float2 uu[32];
+            stage2_load_fft<R>(E, uu, lane);
+            team_bar(bar_id);
+            stage2_store_tile(uu, tile, nyq, lane, h);
+        } else {
+            stage2_forward<R>(E, E, lane);
         }
-        team_bar(bar_id);                                            // the row is complete
-        if constexpr (tc) {
-            if (t < a.t_g) {
-                const long long frame = (long long)clip * a.t_g + t;
-                gcc_tc_copy_out(S0, S1, a.gcc_rows, (frame / 21) * 128 + (frame % 21) * 6, lane, h ? 2 : 0, h ? 3 : 2);
-                float* lm = a.gcc_logmel + frame * (a.n_mels * 4);     // log-mel only; gcc_gemm writes the feature row
-                for (int e = u; e < a.n_mels * 4; e += TL) lm[e] = acc[(e >> 2) * C + (e & 3)];
+    };
+    // fused GCC: is a channel of this warp's pair exactly zero over the whole windowed frame?  (the reference's phase
+    // transform of a dead microphone is a sign pattern of the live partner, extract_core.cuh: dead_pair)
+    auto note_dead = [&](const float2* v) {
+        if constexpr (FUSED) {
+            unsigned ox = 0, oy = 0;
+#pragma unroll
+            for (int n2 = 0; n2 < R; ++n2) { ox |= __float_as_uint(v[n2].x); oy |= __float_as_uint(v[n2].y); }
+            const unsigned dx = __all_sync(0xffffffffu, (ox << 1) == 0), dy = __all_sync(0xffffffffu, (oy << 1) == 0);
+            if (lane == 0) dead_flags[h] = dx | (dy << 1);
+        }
+    };
+
+    // everything after the team's two packed FFTs: mel pieces, gather, GCC, row store, running clip maximum.
+    // mine: this team has a frame; part (fused GCC only): the partner team has one whose accumulator this team helps read.
+    auto finish_frame = [&](bool mine, bool part, int clip, int t, float* row) {
+        float mx = -INFINITY;
+        if constexpr (FUSED) {
+            if (mine) {
+                team_bar(bar_id);                                        // both spectra are in the tile
+                const unsigned dead = dead_flags[0] | (dead_flags[1] << 2);
+                if (dead) bin_phase_gcc_fused<true>(tile, nyq, tb, X, u, taddr + TMEM_COL_W01, dead);
+                else bin_phase_gcc_fused<false>(tile, nyq, tb, X, u, taddr + TMEM_COL_W01, 0u);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the phasor rows -> visible to the tensor core
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                team_bar(bar_id);
+                if (h == 0) {
+                    if (elect_one()) gcc_issue_mma(smem_addr(tile), taddr - ((32u * (warp & 3)) << 16), team, smem_addr(&s_mbar[team]));
+                    __syncwarp();
+                }
+                mx = gather_lanes<MODE>(X, tb, acc, a.n_mels, u);       // log-mel while the MMAs run
+                mbar_wait_parity(smem_addr(&s_mbar[team]), par_mine);
+                par_mine ^= 1u;
             }
+            if (part) {
+                mbar_wait_parity(smem_addr(&s_mbar[pteam]), par_part);
+                par_part ^= 1u;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (mine) gcc_epilogue(taddr, team, warp & 3, lane, acc);
+            if (part) gcc_epilogue(taddr, pteam, warp & 3, lane, acc_part);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            pair_bar(9 + (team >> 1));                                   // both rows are complete; both accumulators are free
+            if (!mine) return;
+        } else {
+            team_bar(bar_id);                                            // both spectra are in place
+            bin_phase<R, MODE, TM>(S0, S1, tb, X, 1e-8f, u, taddr + TMEM_COL_W01);
+            team_bar(bar_id);
+            mx = a.seg_major ? gather_lanes<MODE>(X, tb, acc, a.n_mels, u) : gather_phase<MODE>(X, tb, acc, a.n_mels, u);
+            if constexpr (MODE == MODE_MIC) {
+                team_bar(bar_id);                                        // pieces consumed: X is the GCC exchange buffer now
+                if (h == 0) {
+                    gcc_stage1<R, 0>(S0, S1, X, lane);
+                    __syncwarp();
+                    gcc_stage2<R, 0>(X, tb, acc, a.n_mels, lane);
+                    __syncwarp();
+                    gcc_stage1<R, 1>(S0, S1, X, lane);
+                    __syncwarp();
+                    gcc_stage2<R, 1>(X, tb, acc, a.n_mels, lane);
+                    __syncwarp();
+                    gcc_stage1<R, 2>(S0, S1, X, lane);
+                    __syncwarp();
+                    gcc_stage2<R, 2>(X, tb, acc, a.n_mels, lane);
+                    __syncwarp();
+                    for (int i = lane; i < a.x_zero_f2; i += 32) X[i] = make_float2(0.f, 0.f);   // X goes back to being the piece buffer
+                }
+            }
+            team_bar(bar_id);                                            // the row is complete
         }
         // (an asynchronous bulk store of the row -- fence.proxy.async + cp.async.bulk shared -> global by one lane -- measured
         //  no faster than these 128-bit copies: 9.99 vs 9.93 ms)
-        if (!tc && row != nullptr) store_row(acc, row_elems, row, u, TL);
+        if (row != nullptr) store_row(acc, row_elems, row, u, TL);
+        // a NaN log-mel value makes the clip maximum NaN (reference: db.max(), feature_extractor.py:65-71)
+        const bool nan_any = __any_sync(0xffffffffu, mx != mx);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if (clip != run_clip) {
-            if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], float_to_key(run_max));
+            if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], run_nan ? kNanKey : float_to_key(run_max));
             run_clip = clip;
             run_max = -INFINITY;
+            run_nan = false;
         }
         run_max = fmaxf(run_max, mx);
+        run_nan = run_nan || nan_any;
     };
 
     if constexpr (EDGE) {
+        // edge frame j of a clip -> frame index t; -1 for the zero padding rows past the last frame
+        auto edge_t = [&](long long g) -> int {
+            const int j = int(g % a.frames_per_clip);
+            return (j < a.t_lo) ? j : a.t_hi + (j - a.t_lo);
+        };
         for (long long sc = blockIdx.x; sc < a.n_super; sc += gridDim.x) {
-            const long long g0 = sc * a.fsc + team * a.fpw;
-            for (int i = 0; i < a.fpw && team * a.fpw + i < a.fsc; ++i) {
-                const long long g = g0 + i;
-                if (g >= total_frames) break;
-                const int clip = int(g / a.frames_per_clip);
-                const int j = int(g - (long long)clip * a.frames_per_clip);
-                const int t = (j < a.t_lo) ? j : a.t_hi + (j - a.t_lo);
-                float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
-                if (t >= a.t_raw) {                   // zero padding rows (reference :142-145)
-                    for (int e = u; e < row_elems; e += TL) row[e] = 0.f;
-                    continue;
-                }
-                ClipSrc src;
-                src.base = a.wav + (long long)clip * 4 * a.n_samples;
-                src.n_samples = a.n_samples;
-                if (a.layout == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
-                else { src.chan_stride = 1; src.samp_stride = 4; }
-                const long long start = (long long)t * a.hop - G::N / 2 + a.origin;
-                {
-                    float wreg[R];
-                    if constexpr (TM) {
-                        tmem_ld16(taddr + TMEM_COL_WIN, wreg);
-                        tmem_ld16(taddr + TMEM_COL_WIN + 16, wreg + 16);
+            for (int i = 0; i < a.fpw; ++i) {
+                const long long g = sc * a.fsc + team * a.fpw + i;
+                const long long gp = sc * a.fsc + pteam * a.fpw + i;
+                const bool in_range = g < total_frames;
+                const bool part = FUSED && gp < total_frames && edge_t(gp) < a.t_raw;
+                if (!in_range && !part) continue;
+                int clip = 0, t = 0;
+                float* row = nullptr;
+                bool mine = false;
+                if (in_range) {
+                    clip = int(g / a.frames_per_clip);
+                    t = edge_t(g);
+                    row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
+                    if (t >= a.t_raw) {                   // zero padding rows (reference :142-145)
+                        for (int e = u; e < row_elems; e += TL) row[e] = 0.f;
                     } else {
-#pragma unroll
-                        for (int n2 = 0; n2 < R; ++n2) wreg[n2] = wlane[32 * n2];
+                        mine = true;
                     }
-                    float2 v[R];
-                    if (a.layout == LAYOUT_PCM16_LC)
-                        stage1_load_reflect_pcm16<R>(reinterpret_cast<const short*>(a.wav) + (long long)clip * 4 * a.n_samples,
-                                                     a.n_samples, h, start, wreg, v, lane);
-                    else
-                        stage1_load_reflect<R>(src, 2 * h, 2 * h + 1, start, wreg, v, lane);
-                    if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
-                    else stage1_fft_store<R>(v, tb, E, lane);
                 }
-                __syncwarp();
-                stage2_forward<R>(E, E, lane);
-                finish_frame(clip, t, row);
+                if (mine) {
+                    ClipSrc src;
+                    src.base = a.wav + (long long)clip * 4 * a.n_samples;
+                    src.n_samples = a.n_samples;
+                    if (a.layout == LAYOUT_PLANAR_CL) { src.chan_stride = a.n_samples; src.samp_stride = 1; }
+                    else { src.chan_stride = 1; src.samp_stride = 4; }
+                    const long long start = (long long)t * a.hop - G::N / 2 + a.origin;
+                    {
+                        float wreg[R];
+                        if constexpr (TM) {
+                            tmem_ld16(taddr + TMEM_COL_WIN, wreg);
+                            tmem_ld16(taddr + TMEM_COL_WIN + 16, wreg + 16);
+                        } else {
+#pragma unroll
+                            for (int n2 = 0; n2 < R; ++n2) wreg[n2] = wlane[32 * n2];
+                        }
+                        float2 v[R];
+                        if (a.layout == LAYOUT_PCM16_LC)
+                            stage1_load_reflect_pcm16<R>(reinterpret_cast<const short*>(a.wav) + (long long)clip * 4 * a.n_samples,
+                                                         a.n_samples, h, start, wreg, v, lane);
+                        else
+                            stage1_load_reflect<R>(src, 2 * h, 2 * h + 1, start, wreg, v, lane);
+                        note_dead(v);
+                        if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
+                        else stage1_fft_store<R>(v, tb, E, lane);
+                    }
+                    __syncwarp();
+                    stage2();
+                }
+                if (mine || part) finish_frame(mine, part, clip, t, row);
             }
         }
     } else {
@@ -322,9 +441,9 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         long long sc = blockIdx.x;
         const long long sc_end = a.n_super;
         int fi = 0;
-        auto frame_index = [&](long long s, int i) -> long long {       // -1 past the end
-            if (s >= sc_end || team * a.fpw + i >= a.fsc) return -1;
-            const long long g = s * a.fsc + team * a.fpw + i;
+        auto frame_index = [&](long long s, int i, int tm) -> long long {       // -1 past the end
+            if (s >= sc_end || tm * a.fpw + i >= a.fsc) return -1;
+            const long long g = s * a.fsc + tm * a.fpw + i;
             return g < total_frames ? g : -1;
         };
         float2 raw[R];
@@ -350,7 +469,8 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         // them after the bin phase spills 376 B (12.3 ms instead of 9.2); staging them through tensor memory four taps per
         // bin step (tcgen05.st, then four tcgen05.ld at the next frame) couples the load latency into the team barriers (10.5 ms)
         constexpr bool PREFETCH = !(R == 32 && MODE == MODE_FOA);
-        long long g = frame_index(sc, fi);
+        long long g = frame_index(sc, fi, team);
+        long long gpart = FUSED ? frame_index(sc, fi, pteam) : -1;
         if (PREFETCH && g >= 0) request(g);
         // Consecutive frames share R - 15 taps per lane (hop 480 = 15 * 32 samples: tap n2 of frame t + 1 is tap n2 + 15 of
         // frame t).  The 16-warp kernel parks those 17 taps in its own tensor-memory columns and fetches only the 15 new
@@ -363,7 +483,17 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         // (prefetching just the 15 new taps of the next frame in 30 registers was tried on top of this: 104 B of spills and
         //  9.58 ms instead of 9.06)
 #pragma unroll 1
-        while (g >= 0) {
+        while (g >= 0 || gpart >= 0) {
+            const bool mine = g >= 0;
+            if (++fi == a.fpw) { fi = 0; sc += sc_step; }
+            const long long g_next = frame_index(sc, fi, team);
+            const long long gpart_next = FUSED ? frame_index(sc, fi, pteam) : -1;
+            if (!mine) {                                  // (fused GCC) only the partner has a frame left: help read its accumulator
+                finish_frame(false, true, 0, 0, nullptr);
+                g = g_next;
+                gpart = gpart_next;
+                continue;
+            }
             if constexpr (!PREFETCH) {
                 if constexpr (KEEP) {
                     clip = int(g / a.frames_per_clip);
@@ -416,20 +546,20 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                 if constexpr (LAYOUT == LAYOUT_PCM16_LC) apply_window_pcm16<R, 32>(raw, 0, wlane, v);
                 else apply_window<R, 32>(raw, wlane, v);
             }
+            note_dead(v);
             const int clip_now = clip, t_now = t;
             float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
-            if (++fi == a.fpw || team * a.fpw + fi >= a.fsc) { fi = 0; sc += sc_step; }
-            const long long g_next = frame_index(sc, fi);
             if (PREFETCH && g_next >= 0) request(g_next);
             if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
             else stage1_fft_store<R>(v, tb, E, lane);
             __syncwarp();
-            stage2_forward<R>(E, E, lane);
-            finish_frame(clip_now, t_now, row);
+            stage2();
+            finish_frame(true, gpart >= 0, clip_now, t_now, row);
             g = g_next;
+            gpart = gpart_next;
         }
     }
-    if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], float_to_key(run_max));
+    if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], run_nan ? kNanKey : float_to_key(run_max));
     if constexpr (TM) {
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();
@@ -457,6 +587,7 @@ static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream)
         const int n = atoi(e) / 2;
         if (n >= 1 && n < teams) teams = n;
     }
+    if (SP::tc) teams &= ~1;                              // fused GCC: teams work in pairs (extract_kernel)
     if (teams < 1) { set_error("n_mels too large for the shared-memory budget"); return SELD_EUNSUPPORTED; }
     a.fpw = frames_per_team((R == 32 && MODE == MODE_FOA && !EDGE) ? 8 : 2);
     a.fsc = teams * a.fpw;
@@ -488,22 +619,8 @@ static int launch_kernels(const seld_plan* plan, const ExtractArgs& a, cudaStrea
 template <int R, int MODE>
 static int launch_mode(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
     constexpr bool can_tc = (MODE == MODE_MIC && R == 32);
-    if (!(can_tc && a.gcc_tc)) return launch_kernels<R, MODE, false>(plan, a, stream);
-    int rc = launch_kernels<R, MODE, can_tc>(plan, a, stream);
-    if (rc != SELD_OK) return rc;
-    GccGemmArgs g{};
-    g.A = reinterpret_cast<const __half*>(a.gcc_rows);
-    g.Bt = reinterpret_cast<const __half*>(plan->gcc_bt);
-    g.n_frames = (long long)a.n_clips * a.t_g;
-    g.n_tiles = (g.n_frames + 20) / 21;
-    g.scale = 1.0f / 512.0f;
-    g.dense_out = nullptr;
-    g.dense_rows = 0;
-    g.feat = a.out;
-    g.logmel = a.gcc_logmel;
-    g.frames_per_clip = a.t_g;
-    g.t_out = a.t_out;
-    return launch_gcc_gemm(g, plan->num_sms, stream);
+    if (can_tc && a.gcc_tc) return launch_kernels<R, MODE, can_tc>(plan, a, stream);
+    return launch_kernels<R, MODE, false>(plan, a, stream);
 }
 
 template <int R>
@@ -620,8 +737,8 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
         return cuda_fail(e, "plan table upload");
     }
     if (e == cudaSuccess && mode == SELD_MODE_MIC && n_fft == 1024 && n_mels == 64) {
-        // B^T of the tensor-core lag projection: [64 lags][1024] fp16, x512 (see gcc_gemm.cu / seld_b200.tables.gcc_basis)
-        // stored as the operand image gcc_gemm.cu bulk-copies: [16 chunks][64 rows][128 bytes, 16-byte units XOR (row % 8)]
+        // basis of the tensor-core lag projection (extract_core.cuh): [64 lags][K = 1024] fp16, x512, row-major.
+        // K = 0: Re P[0], K = 1: Re P[512] (rides in the unused Im P[0] slot), K = 2k / 2k + 1: Re / Im P[k].
         std::vector<__half> bt((size_t)64 * 1024);
         const double two_pi = 2.0 * 3.14159265358979323846264338327950288;
         for (int j = 0; j < 64; ++j) {
@@ -635,9 +752,7 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
                     const double ang = two_pi * double(k) * double(lag) / 1024.0;
                     val = (K & 1) ? -sin(ang) : cos(ang);                  // 512 * (2/1024) * {cos, -sin}
                 }
-                const int c = K >> 6, kk = K & 63;
-                const size_t idx = (size_t)c * 4096 + (size_t)j * 64 + (size_t)(((kk >> 3) ^ (j & 7)) << 3) + (kk & 7);
-                bt[idx] = __float2half(float(val));
+                bt[(size_t)j * 1024 + K] = __float2half(float(val));
             }
         }
         up((void**)&plan->gcc_bt, bt.data(), sizeof(__half) * bt.size());
@@ -685,16 +800,6 @@ int64_t seld_plan_num_frames(seld_plan_t plan, int64_t n_samples) {
     return 1 + n_samples / plan->hop;
 }
 
-static int64_t workspace_bytes_for(const seld_plan* plan, int n_clips, int64_t n_samples, int t_out, bool centered = true) {
-    if (!plan || plan->gcc_bt == nullptr || n_clips <= 0 || n_samples <= 0 || t_out <= 0) return 0;
-    if (!centered && n_samples < plan->n_fft) return 0;
-    const int64_t t_raw = centered ? 1 + n_samples / plan->hop : 1 + (n_samples - plan->n_fft) / plan->hop;
-    const int64_t t_g = t_raw < t_out ? t_raw : t_out;
-    const int64_t frames = (int64_t)n_clips * t_g;
-    const int64_t tiles = (frames + 20) / 21;            // 21 frames (126 rows of 2 KB fp16 phasors) per 128-row tile
-    return tiles * 128 * 2048 + frames * 64 * 4 * 4;     // + the log-mel side buffer
-}
-
 static int extract_common(seld_plan_t plan, const void* wav_void, int layout, int n_clips, int64_t n_samples, int t_out,
                           float* feat_raw_dev, uint32_t* clip_max_key_dev, void* workspace_dev, int64_t workspace_bytes,
                           void* stream, bool centered = true) {
@@ -730,17 +835,11 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
     a.slot1 = plan->slot1;
     a.ov = plan->ov;
     a.pb = plan->pb;
-    a.t_g = a.t_raw < t_out ? a.t_raw : t_out;
-    {
-        const int64_t need = workspace_bytes_for(plan, n_clips, n_samples, t_out, centered);
-        a.gcc_tc = (need > 0 && workspace_dev != nullptr && workspace_bytes >= need &&
-                    reinterpret_cast<uintptr_t>(workspace_dev) % 16 == 0) ? 1 : 0;
-        a.gcc_rows = static_cast<float*>(workspace_dev);
-        {
-            const int64_t frames = (int64_t)n_clips * a.t_g;
-            a.gcc_logmel = a.gcc_rows + ((frames + 20) / 21) * 128 * 512;
-        }
-    }
+    // MIC at the production geometry: the lag projection runs on the tensor cores inside the extractor (no scratch).
+    // workspace_bytes < 0 asks for the CUDA-core inverse transforms instead (tests compare the two).
+    (void)workspace_dev;
+    a.gcc_tc = (plan->gcc_bt != nullptr && plan->seg_major && workspace_bytes >= 0) ? 1 : 0;
+    a.gcc_basis = plan->gcc_bt;
     a.seg_major = plan->seg_major;
     a.x_zero_f2 = plan->seg_major ? plan->n_slots * (plan->mode == SELD_MODE_FOA ? PieceGeo<MODE_FOA>::PSTRIDE : PieceGeo<MODE_MIC>::PSTRIDE) : 0;
     // frames [t_lo, t_hi) need no reflection: t*hop - n_fft/2 >= 0 and t*hop + n_fft/2 <= n_samples
@@ -765,7 +864,8 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
 }
 
 int64_t seld_extract_workspace_bytes(seld_plan_t plan, int n_clips, int64_t n_samples, int t_out) {
-    return workspace_bytes_for(plan, n_clips, n_samples, t_out);
+    (void)plan; (void)n_clips; (void)n_samples; (void)t_out;
+    return 0;           // the fused tensor-core GCC path needs no scratch (kept for ABI stability)
 }
 
 int seld_extract(seld_plan_t plan, const float* wav_dev, int layout, int n_clips, int64_t n_samples, int t_out,

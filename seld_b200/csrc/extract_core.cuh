@@ -470,10 +470,7 @@ SELD_HD float pack_half2(float lo, float hi) {          // two floats -> one 32-
 #endif
 }
 
-// GCC_TC (MIC only): instead of per-channel unit phasors for the CUDA-core inverse transforms, write the six PAIR
-// phasors exp(i angle(conj(X_m) X_n)) = conj(u_m) u_n as fp16 (re, im) words into the bin's own four spectrum slots -- the A operand
-// rows of the tensor-core lag projection (gcc_gemm.cu), copied out by gcc_tc_copy_out.
-template <int R, int MODE, bool GCC_TC = false, bool W_TMEM = false>
+template <int R, int MODE, bool W_TMEM = false>
 SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, float eps, int u,      // u: team lane, 0..TL-1
                        unsigned taddr_w01 = 0) {                                                    // W_TMEM: mel weights from tensor memory
     using G = Geo<R>;
@@ -517,29 +514,7 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
             val[5] = iy * inv4;
             val[6] = iz * inv4;
         } else {
-            if (valid && GCC_TC) {
-                // per-channel unit phasors from the powers the log-mel block needs anyway (one MUFU.RSQ each; |X|^2 stays in
-                // range for any spectrum a float can hold), then six complex products; a pair with a zero channel is 1
-                float2 uc[4];
-                bool zc[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    zc[c] = !(val[c] >= 1.17549435e-38f);
-                    const float inv = rsqrt_ftz(val[c]);
-                    uc[c] = pmul(ch[c], make_float2(inv, inv));
-                }
-                const float2 p01 = unit_pair(uc[0], uc[1], zc[0] || zc[1]), p02 = unit_pair(uc[0], uc[2], zc[0] || zc[2]);
-                const float2 p03 = unit_pair(uc[0], uc[3], zc[0] || zc[3]), p12 = unit_pair(uc[1], uc[2], zc[1] || zc[2]);
-                const float2 p13 = unit_pair(uc[1], uc[3], zc[1] || zc[3]), p23 = unit_pair(uc[2], uc[3], zc[2] || zc[3]);
-                if (k == 0 || k == N / 2) {          // real bins: six real parts as three half2 words
-                    S0[k] = make_float2(pack_half2(p01.x, p02.x), pack_half2(p03.x, p12.x));
-                    S1[k] = make_float2(pack_half2(p13.x, p23.x), 0.f);
-                } else {
-                    S0[k] = make_float2(pack_half2(p01.x, p01.y), pack_half2(p02.x, p02.y));
-                    S0[kn] = make_float2(pack_half2(p03.x, p03.y), pack_half2(p12.x, p12.y));
-                    S1[k] = make_float2(pack_half2(p13.x, p13.y), pack_half2(p23.x, p23.y));
-                }
-            } else if (valid) {
+            if (valid) {
                 const float2 u0 = unit_phasor(ch[0]), u1 = unit_phasor(ch[1]);
                 const float2 u2 = unit_phasor(ch[2]), u3 = unit_phasor(ch[3]);
                 if (k == 0 || k == N / 2) {          // real bins: both channels of a pair share one slot
@@ -576,6 +551,14 @@ SELD_HD float fast_db(float x) {            // 10 log10(x), x > 0
 #endif
 }
 
+// 10 log10(max(power, 1e-10)) with torch.clamp's NaN behaviour (a NaN power stays NaN: reference :65-71 through amplitude_to_DB)
+SELD_HD float power_to_db(float pw) {
+    const float v = fast_db(fmaxf(pw, 1e-10f));
+    return (pw != pw) ? pw : v;
+}
+// running maximum that a NaN sticks to (torch's max propagates NaN)
+SELD_HD float max_nan(float m, float v) { return (v != v || m != m) ? NAN : fmaxf(m, v); }
+
 // ---------------------------------------------------------------- gather: pieces -> mel rows
 // Team lane u owns filters m = u, u + TL, ...: mel[m][c] = sum_{pieces of seg m} P.x + sum_{pieces of seg m-1} P.y, in
 // piece order.  Log-mel channels get 10 log10(max(., 1e-10)) here; returns the lane's maximum dB.
@@ -602,8 +585,8 @@ SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float v = fast_db(fmaxf(sum[c], 1e-10f));
-            mx = fmaxf(mx, v);
+            const float v = power_to_db(sum[c]);
+            mx = max_nan(mx, v);
             acc[m * C + c] = v;
         }
 #pragma unroll
@@ -663,8 +646,8 @@ SELD_HD float gather_lanes(const float2* P, const Tables& tb, float* acc, int n_
         for (int c = 0; c < NV; ++c) {
             float v = A[c].x + below[c];
             if (c < 4) {
-                v = fast_db(fmaxf(v, 1e-10f));
-                mx = fmaxf(mx, v);
+                v = power_to_db(v);
+                mx = max_nan(mx, v);
             }
             acc[u * C + c] = v;
         }
@@ -672,43 +655,210 @@ SELD_HD float gather_lanes(const float2* P, const Tables& tb, float* acc, int n_
     return mx;
 }
 
-// ---------------------------------------------------------------- tensor-core GCC: copy the A rows out
-// rows: [6][512] 32-bit words (one fp16 (re, im) pair per bin; word 0 = (Re P[0], Re P[N/2])).  Lane l copies bins
-// l, l+32, ...: coalesced 128-byte stores.  N = 1024 only.
+// ---------------------------------------------------------------- fused tensor-core GCC (MIC, n_fft 1024, 64 lags)
+// reference feature_extractor.py:209-211 keeps 64 of the 1024 irfft outputs, so per (frame, pair)
+//     cc[lag] = sum_K basis[lag][K] * P[K],   K = 1024 = (Re P[0], Re P[512], Re P[1], Im P[1], ..., Im P[511])
+// is a [64 x 1024] x [1024 x 6] contraction per frame.  It runs on the tensor cores INSIDE the extractor:
+//   * A operand = the basis (64 lags x 1024, fp16), resident in TENSOR MEMORY for the whole kernel (tcgen05.mma with the A
+//     operand in TMEM): M = 64 occupies lanes 0..15 of each 32-lane subpartition, so two "atoms" interleave -- lanes 0..15
+//     hold K in [0, 512), lanes 16..31 hold K in [512, 1024) -- and the 128 KB basis takes 256 columns (probed on B200:
+//     tools/microbench/probe_tmem_ts.cu; A and D of one MMA must sit on the same datapath lanes).
+//   * B operand = the frame's six pair-phasor rows (N = 8 with two unused rows), written by the bin phase IN PLACE over
+//     the team's spectrum in the no-swizzle K-major core-matrix layout: bin k of row r is the 32-bit word (re, im fp16) at
+//         (k >> 2) * 144 + r * 16 + (k & 3) * 4
+//     (16-byte K units of 8 rows, padded from 128 to 144 bytes: bank = (k + 4 r) mod 32, so both the stage-2 stores --
+//     lane = k mod 32 -- and the bin phase -- lane u owns bins 9u .. 9u + 8 -- are conflict-free).  Before the bin phase the
+//     same words hold the packed spectra: rows 0..3 = Re/Im Z0[k], Re/Im Z0[N-k], rows 4..7 the same of Z1.
+//   * D = 8 fp32 columns per team in TMEM (lower atom + upper atom, summed with one shuffle in the epilogue).
+// One elected thread issues 64 MMAs (M64 N8 K16, 8 cycles each, measured) per frame; nothing of this touches HBM.
 #if defined(__CUDACC__)
-// Destination = the UMMA operand image gcc_gemm.cu bulk-copies straight into shared memory (K-major SWIZZLE_128B):
-// per (tile, chunk of 32 bins) one 16 KB block; row r of the chunk is 128 contiguous bytes at r * 128 and its 16-byte
-// unit u sits at unit position u ^ (r % 8).  Lane l holds bin k = l + 32 * chunk = word l of the row, so every store
-// instruction writes one full 128-byte line.  tile_row = tile * 128 + row-in-tile of the frame's first pair.
-// Slots pp in [pp_lo, pp_hi): the team's first warp copies slots 0 and 1 (both live in S0), the second slot 2 (S1).
-__device__ __forceinline__ void gcc_tc_copy_out(const float2* S0, const float2* S1, float* scratch, long long tile_row,
-                                                int lane, int pp_lo, int pp_hi) {
-    constexpr int N = 1024;
-    const long long tile = tile_row >> 7;
-    const int r_first = int(tile_row & 127);
-    float* tbase = scratch + tile * (16 * 4096);
+constexpr int GT_UNIT = 144;                    // byte pitch of a 16-byte K unit (8 rows)
+constexpr int GT_CHUNK = 8 * GT_UNIT;           // 32 bins
+constexpr int GT_BYTES = 128 * GT_UNIT;         // 512 bins: 18 432 bytes (the two exchange buffers alias its first 17 408)
+constexpr int GT_NYQ_BYTES = 128;               // Nyquist "column": rows 0, 1 = Z0[512], rows 4, 5 = Z1[512]
+constexpr int TMEM_COL_BASIS = 128, TMEM_COL_D = 384;
+
+__device__ __forceinline__ bool elect_one() {   // one lane of a converged warp (lets ptxas issue UTCHMMA without a per-thread loop)
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// stage-2 results of warp h (u[p] = Z_h[32 bitrev(p) + lane]) -> rows 4h .. 4h + 3 of the tile; Z_h[512] -> the Nyquist column
+__device__ __forceinline__ void stage2_store_tile(const float2* u, unsigned char* tile, unsigned char* nyq, int lane, int h) {
+    const int pm = (32 - lane) & 31;                       // k = 32 k1 + lane > 512 mirrors to bin N - k: position 32 - lane
+    unsigned char* bd = tile + (lane >> 2) * GT_UNIT + (lane & 3) * 4 + (4 * h) * 16;
+    unsigned char* bm = tile + (pm >> 2) * GT_UNIT + (pm & 3) * 4 + (4 * h + 2) * 16 + (lane == 0 ? GT_CHUNK : 0);
+    unsigned char* b16 = (lane == 0) ? nyq + (4 * h) * 16 : bm + 15 * GT_CHUNK;
 #pragma unroll
-    for (int pp = 0; pp < 3; ++pp) {                 // slot pp holds pairs 2pp (.x) and 2pp + 1 (.y)
-        if (pp < pp_lo || pp >= pp_hi) continue;
-        const int ra = r_first + 2 * pp, rb = ra + 1;
-        float* dst0 = tbase + ra * 32 + ((((lane >> 2) ^ (ra & 7)) << 2) | (lane & 3));
-        float* dst1 = tbase + rb * 32 + ((((lane >> 2) ^ (rb & 7)) << 2) | (lane & 3));
+    for (int p = 0; p < 32; ++p) {
+        const int k1 = bitrev(p, 5);
+        unsigned char* d = (k1 < 16) ? bd + k1 * GT_CHUNK : (k1 == 16 ? b16 : bm + (31 - k1) * GT_CHUNK);
+        *reinterpret_cast<float*>(d) = u[p].x;
+        *reinterpret_cast<float*>(d + 16) = u[p].y;
+    }
+}
+
+// six pair phasors conj(u_m) u_n of the per-channel unit phasors u_c = X_c / |X_c| (one MUFU.RSQ per channel on the power the
+// log-mel block needs anyway); a pair with a zero channel is 1, as exp(i angle(0)) = 1.  Pair order: reference :207-208.
+__device__ __forceinline__ void pair_phasors(const float2* ch, const float* val, float2* p) {
+    float2 uc[4];
+    bool zc[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {               // i = chunk; this lane's bin k = lane + 32 i
-            const int k = lane + 32 * i;
-            float2 w;
-            if (i == 0 && lane == 0) {
-                // halves 2pp, 2pp+1 of the DC triple and of the Nyquist triple -> words (Re P[0], Re P[512])
-                const unsigned dw = __float_as_uint(pp == 0 ? S0[0].x : (pp == 1 ? S0[0].y : S1[0].x));
-                const unsigned nw = __float_as_uint(pp == 0 ? S0[N / 2].x : (pp == 1 ? S0[N / 2].y : S1[N / 2].x));
-                w.x = __uint_as_float((dw & 0xffffu) | (nw << 16));
-                w.y = __uint_as_float((dw >> 16) | (nw & 0xffff0000u));
-            } else {
-                w = (pp == 0) ? S0[k] : (pp == 1 ? S0[N - k] : S1[k]);
-            }
-            dst0[i * 4096] = w.x;
-            dst1[i * 4096] = w.y;
+    for (int c = 0; c < 4; ++c) {
+        zc[c] = !(val[c] >= 1.17549435e-38f);
+        const float inv = rsqrt_ftz(val[c]);
+        uc[c] = pmul(ch[c], make_float2(inv, inv));
+    }
+    p[0] = unit_pair(uc[0], uc[1], zc[0] || zc[1]);
+    p[1] = unit_pair(uc[0], uc[2], zc[0] || zc[2]);
+    p[2] = unit_pair(uc[0], uc[3], zc[0] || zc[3]);
+    p[3] = unit_pair(uc[1], uc[2], zc[1] || zc[2]);
+    p[4] = unit_pair(uc[1], uc[3], zc[1] || zc[3]);
+    p[5] = unit_pair(uc[2], uc[3], zc[2] || zc[3]);
+}
+
+// The reference on a DEAD channel (an exactly zero spectrum): R = conj(X_m) X_n is a signed zero, torch.angle gives pi where
+// its real part is -0 -- which is where the live partner has Re < 0 and Im < 0 (sign bits; measured on the reference's torch
+// build for either operand order) -- and exp(1j * pi) = (-1, -8.74e-8) in complex64.  Two dead channels give +0 -> 1.
+__device__ __forceinline__ float2 dead_pair(float2 xm, float2 xn, bool dm, bool dn, float2 live_pair) {
+    if (!(dm || dn)) return live_pair;
+    if (dm && dn) return make_float2(1.f, 0.f);
+    const float2 x = dm ? xn : xm;
+    const bool neg = (__float_as_uint(x.x) & __float_as_uint(x.y)) >> 31;
+    return neg ? make_float2(-1.f, -8.742278e-8f) : make_float2(1.f, 0.f);
+}
+
+// Bin phase of the fused MIC kernel: powers -> mel pieces as in bin_phase<MODE_MIC>, pair phasors written in place as the
+// B operand.  DEAD (rare, rolled loop): some channel of this frame is exactly zero (dead bits: bit c = channel c).
+template <bool DEAD>
+__device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const unsigned char* nyq, const Tables& tb, float2* P, int u,
+                                                    unsigned taddr_w01, unsigned dead) {
+    constexpr int N = 1024, BPT = 9, NV = 4, PSTRIDE = PieceGeo<MODE_MIC>::PSTRIDE;
+    const int kbeg = u * BPT;
+    const unsigned long long endmask = tb.endmask[u];
+    int slot = tb.slot0[u], next = tb.slot1[u];
+    float2 acc2[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) acc2[c] = make_float2(0.f, 0.f);
+
+    auto spectra = [&](const unsigned char* col, bool real_bin, float2* ch, float* val) {
+        float f[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) f[r] = *reinterpret_cast<const float*>(col + 16 * r);
+        if (real_bin) { f[2] = f[0]; f[3] = f[1]; f[6] = f[4]; f[7] = f[5]; }      // Z[N - k] is Z[k] itself for k = 0, N/2
+        ch[0] = make_float2(f[0] + f[2], f[1] - f[3]);                             // twice the channel spectra
+        ch[1] = make_float2(f[1] + f[3], f[2] - f[0]);
+        ch[2] = make_float2(f[4] + f[6], f[5] - f[7]);
+        ch[3] = make_float2(f[5] + f[7], f[6] - f[4]);
+        if constexpr (DEAD) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if ((dead >> c) & 1u) ch[c] = make_float2(0.f, 0.f);
         }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) val[c] = fmaf(ch[c].x, ch[c].x, ch[c].y * ch[c].y);
+    };
+    auto phasors = [&](const float2* ch, const float* val, float2* p) {
+        pair_phasors(ch, val, p);
+        if constexpr (DEAD) {
+            constexpr int PM[6] = {0, 0, 0, 1, 1, 2}, PN[6] = {1, 2, 3, 2, 3, 3};
+#pragma unroll
+            for (int q = 0; q < 6; ++q) p[q] = dead_pair(ch[PM[q]], ch[PN[q]], (dead >> PM[q]) & 1u, (dead >> PN[q]) & 1u, p[q]);
+        }
+    };
+    auto step = [&](int i, bool first, bool last) {
+        const int k = kbeg + i;
+        const bool valid = k <= N / 2;
+        // bins past N/2 (lanes 57 .. 63) carry zero weights and never close a piece: they read the Nyquist column
+        const unsigned char* col = (k >= N / 2) ? nyq : tile + 36 * k - 32 * (k & 3);
+        float2 ch[4];
+        float val[NV];
+        spectra(col, (first && k == 0) || (last && k >= N / 2), ch, val);
+        if (valid && k < N / 2) {
+            float2 p[6];
+            phasors(ch, val, p);
+            float w[6];
+            if (first && k == 0) {                       // lane 0: the DC and Nyquist bins are real and share word 0 of each row
+                float2 chn[4], pn[6];
+                float valn[NV];
+                spectra(nyq, true, chn, valn);
+                phasors(chn, valn, pn);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, pn[q].x);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, p[q].y);
+            }
+            float* dst = reinterpret_cast<float*>(tile + 36 * k - 32 * (k & 3));
+#pragma unroll
+            for (int q = 0; q < 6; ++q) dst[4 * q] = w[q];
+        }
+        float2 wt;
+        tmem_ld2(taddr_w01 + 2 * i, wt.x, wt.y);
+#pragma unroll
+        for (int c = 0; c < NV; ++c) acc2[c] = pfma(make_float2(val[c], val[c]), wt, acc2[c]);
+        const unsigned flag = static_cast<unsigned>(endmask >> i) & 1u;
+        piece_flush<NV>(acc2, P + slot * PSTRIDE, flag);
+        slot = flag ? next : slot;
+        next += int(flag);
+    };
+    if constexpr (DEAD) {
+#pragma unroll 1
+        for (int i = 0; i < BPT; ++i) step(i, i == 0, i == BPT - 1);
+    } else {
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) step(i, i == 0, i == BPT - 1);
+    }
+}
+
+// kind::f16 MMA with the A operand in tensor memory: D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void mma_f16_ts(unsigned d_tmem, unsigned a_tmem, unsigned long long b_desc, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Issued by ONE elected thread once the team's phasor rows are in place (and fenced to the async proxy): 32 MMAs of
+// K = 16 per atom; tcgen05.commit arrives on the team's mbarrier when all of them have read the tile and written D.
+__device__ __forceinline__ void gcc_issue_mma(unsigned tile_saddr, unsigned tmem_base, int team, unsigned mbar_saddr) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    constexpr unsigned idesc = (1u << 4) | ((8u >> 3) << 17) | ((64u >> 4) << 24);        // F32 accumulate, F16 x F16, K-major, N = 8, M = 64
+    // no-swizzle K-major descriptor (cute::UMMA::SmemDescriptor): start address, LBO = 144 (K-adjacent core matrices),
+    // SBO (8-row groups; a single group here), version 1
+    const unsigned long long desc = (unsigned long long)((tile_saddr >> 4) & 0x3FFF) | ((unsigned long long)(GT_UNIT >> 4) << 16) |
+                                    ((unsigned long long)(GT_CHUNK >> 4) << 32) | (1ull << 46);
+    const unsigned d_lo = tmem_base + TMEM_COL_D + 8 * team, a_lo = tmem_base + TMEM_COL_BASIS;
+    const unsigned up = 16u << 16;
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {
+        mma_f16_ts(d_lo, a_lo + 8 * s, desc + (unsigned long long)((2 * GT_UNIT * s) >> 4), idesc, s > 0);
+        mma_f16_ts(d_lo + up, a_lo + up + 8 * s, desc + (unsigned long long)((2 * GT_UNIT * (32 + s)) >> 4), idesc, s > 0);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar_saddr) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_parity(unsigned bar_saddr, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar_saddr), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// Epilogue of one team's accumulator, executed by every warp of the team PAIR (four warps = the four TMEM subpartitions):
+// warp quadrant q holds lags 16 q .. 16 q + 15 -- K < 512 partial sums in lanes 0..15, K >= 512 in lanes 16..31.  The six
+// GCC channels of a lag are 24 contiguous bytes of the staged feature row.
+__device__ __forceinline__ void gcc_epilogue(unsigned taddr_quadrant, int team, int q, int lane, float* acc_row) {
+    float v[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "r"(taddr_quadrant + TMEM_COL_D + 8 * team) : "memory");
+#pragma unroll
+    for (int n = 0; n < 6; ++n) v[n] = (v[n] + __shfl_xor_sync(0xffffffffu, v[n], 16)) * (1.0f / 512.0f);     // the basis is stored x512
+    if (lane < 16) {
+        float2* d = reinterpret_cast<float2*>(acc_row + (16 * q + lane) * 10 + 4);
+        d[0] = make_float2(v[0], v[1]);
+        d[1] = make_float2(v[2], v[3]);
+        d[2] = make_float2(v[4], v[5]);
     }
 }
 #endif

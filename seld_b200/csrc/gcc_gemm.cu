@@ -1,4 +1,4 @@
-// GCC-PHAT lag projection on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+// Stand-alone GCC-PHAT lag projection on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a: seld_gcc_gemm.
 //
 // reference feature_extractor.py:209-211 computes, per microphone pair and frame,
 //     cc = irfft(exp(1j * angle(R)))[lags -32..31]
@@ -9,16 +9,17 @@
 // and B = the matching rows of the inverse DFT basis (seld_b200/tables.py: gcc_basis).  FP16 operands with FP32
 // accumulation keep the result within ~5e-5 of the float32 irfft (tolerance 1e-3).
 //
-// Kernel: one CTA = 128 threads owns M = 128 rows at a time.  K is walked in 16 chunks of 64; each chunk of A (128 x 64
-// halfs = 16 KB, read from the phasor scratch rows the extractor wrote) and of B^T (64 x 64 halfs = 8 KB, L2 resident)
-// is brought into shared memory with coalesced 16-byte cp.async in a (padded) no-swizzle K-major core-matrix layout, three
-// stages deep; one elected thread issues 4 x tcgen05.mma (M128 N64 K16, kind::f16) per chunk accumulating in 64 TMEM
-// columns, and tcgen05.commit on the stage's mbarrier tells the loaders when the stage may be overwritten.  The epilogue
-// reads the accumulator with tcgen05.ld (warp w owns TMEM lanes 32w..32w+31 = its 32 rows), scales, and scatters the 64
-// lags of each row into the GCC channel of the feature tensor ([t][mel = lag index][4 + pair]).
+// The extractor no longer calls this kernel: it runs the same contraction per frame INSIDE extract_kernel, with the basis
+// resident in tensor memory and the phasor rows never leaving shared memory (extract_core.cuh, "fused tensor-core GCC").
+// This file keeps the dense [rows, 1024] x [1024, 64] form behind the C ABI for callers that hold phasor rows in HBM, and
+// as the numerical pin of the fp16 basis (tests/test_gpu_gcc_gemm.py).
+//
+// Kernel: persistent CTAs of 192 threads, M = 128 rows per tile, K walked in 16 chunks of 64.  Warp 4 = producer: one
+// cp.async.bulk per operand per chunk (both operands arrive as ready-made K-major SWIZZLE_128B images) into a 3-stage
+// mbarrier ring; warp 5 = one ELECTED thread issuing 4 x tcgen05.mma (M128 N64 K16, kind::f16) per chunk and
+// tcgen05.commit to free the stage; warps 0-3 = epilogue (tcgen05.ld, warp w <-> TMEM lanes 32w..32w+31); the accumulator
+// is double-buffered in TMEM so tile i+1's MMAs overlap tile i's epilogue.
 #include <cuda_fp16.h>
-
-#include <atomic>
 
 #include "plan.h"
 
@@ -33,8 +34,6 @@ constexpr int GSTAGES = 3;
 constexpr int GA_BYTES = GM * GKC * 2;       // 16 KB
 constexpr int GB_BYTES = GN * GKC * 2;       // 8 KB
 constexpr int GSTAGE_BYTES = GA_BYTES + GB_BYTES;
-constexpr int GSTAGING_BYTES = 21 * GN * 6 * 4;          // epilogue staging G[frame][lag][pair]
-constexpr int kFramesPerTile = 21;     // fused path: 21 frames x 6 pairs = 126 of the 128 rows (rows 126, 127 are padding)
 // Operand images.  Both operands arrive in global memory ALREADY in the shared-memory image of the canonical K-major
 // SWIZZLE_128B UMMA layout, one contiguous block per (tile, chunk): row r of a chunk is 128 contiguous bytes at r * 128,
 // its 16-byte unit u stored at unit position u ^ (r % 8) (Swizzle<3,4,3>); 8-row atoms are 1024 bytes apart (SBO).  One
@@ -84,18 +83,20 @@ __device__ __forceinline__ unsigned long long umma_desc_sw128(uint32_t saddr) {
 // kind::f16 instruction descriptor: F32 accumulate, F16 x F16, both K-major, N = 64, M = 128 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t kIdesc = (1u << 4) | ((GN >> 3) << 17) | ((GM >> 4) << 24);
 
-struct GccGemmArgs {          // (also declared in extract.cu, which drives the kernel in fused mode)
+struct GccGemmArgs {
     const __half* A;          // operand image [tile][16 chunks][16 KB]
     const __half* Bt;         // operand image [16 chunks][8 KB]
     long long n_tiles;
     float scale;              // epilogue factor (the basis is stored x512)
-    float* dense_out;         // dense mode: [n_tiles * 128][64]; nullptr in fused mode
-    long long dense_rows;     // dense mode: valid rows
-    float* feat;              // fused mode: feature tensor [clip][t_out][64][10]
-    const float* logmel;      // fused mode: [frame][64 mels][4] un-clamped log-mel written by the extractor
-    long long n_frames;       // fused mode: frames with a stored row; tile t holds frames [21 t, 21 t + 21)
-    int frames_per_clip, t_out;
+    float* dense_out;         // [n_tiles * 128][64]
+    long long dense_rows;     // valid rows
 };
+
+__device__ __forceinline__ bool elect_one_lane() {      // one lane of a converged warp: lets ptxas issue UTCHMMA without a per-thread loop
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter w), warp 4 bulk-copy producer, warp 5 MMA issuer.
 __global__ void __launch_bounds__(192) gcc_gemm_kernel(GccGemmArgs g) {
@@ -104,7 +105,6 @@ __global__ void __launch_bounds__(192) gcc_gemm_kernel(GccGemmArgs g) {
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t base = (smem_u32(gsm) + 1023u) & ~1023u;      // SWIZZLE_128B atoms must be 1024-byte aligned
-    float* G = reinterpret_cast<float*>(gsm + (base - smem_u32(gsm)) + GSTAGES * GSTAGE_BYTES);
 
     if (tid == 0) {
         for (int s = 0; s < GSTAGES; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
@@ -138,7 +138,9 @@ __global__ void __launch_bounds__(192) gcc_gemm_kernel(GccGemmArgs g) {
         }
     } else if (warp == 5) {
         // ---------------- MMA issuer: 4 x (M128 N64 K16) per chunk into TMEM accumulator (tile parity)
-        if (lane == 0) {
+        // (an `if (lane == 0)` here makes ptxas wrap every UTCHMMA in a per-thread ELECT loop: ~60 cycles per MMA, measured
+        //  with tools/microbench/probe_tmem_ts.cu; elect.sync issues them back to back)
+        if (elect_one_lane()) {
             uint32_t q = 0, lt = 0;
             for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++lt) {
                 const uint32_t as = lt & 1;
@@ -195,44 +197,13 @@ __global__ void __launch_bounds__(192) gcc_gemm_kernel(GccGemmArgs g) {
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_acc_empty[as]));      // the MMA warp may reuse this accumulator
 
-            if (g.dense_out != nullptr) {
-                const long long row = tile * GM + tid;
-                if (row < g.dense_rows) {
-                    float4* d4 = reinterpret_cast<float4*>(g.dense_out + row * GN);
+            const long long row = tile * GM + tid;
+            if (row < g.dense_rows) {
+                float4* d4 = reinterpret_cast<float4*>(g.dense_out + row * GN);
 #pragma unroll
-                    for (int n = 0; n < GN; n += 4)
-                        d4[n / 4] = make_float4(__uint_as_float(v[n]) * g.scale, __uint_as_float(v[n + 1]) * g.scale,
-                                                __uint_as_float(v[n + 2]) * g.scale, __uint_as_float(v[n + 3]) * g.scale);
-                }
-            } else {
-                // Fused mode: assemble COMPLETE feature rows [mel][4 log-mel + 6 GCC] so every 32-byte sector is written
-                // whole (scattering only the GCC channels forces a DRAM read-modify-write of the rows).  Stage the tile as
-                // G[frame][lag][pair], then the 128 threads walk (frame, lag) groups: 16 bytes of log-mel from the side
-                // buffer + 24 bytes from G -> 40 contiguous bytes.
-                if (tid < kFramesPerTile * 6) {
-                    const int fl = tid / 6, pr = tid - fl * 6;
-#pragma unroll
-                    for (int n = 0; n < GN; ++n) G[(fl * GN + n) * 6 + pr] = __uint_as_float(v[n]) * g.scale;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int idx = tid; idx < kFramesPerTile * GN; idx += 128) {
-                    const int fl = idx / GN, n = idx - fl * GN;
-                    const long long frame = tile * kFramesPerTile + fl;
-                    if (frame < g.n_frames) {
-                        const long long clip = frame / g.frames_per_clip;
-                        const int t = int(frame - clip * g.frames_per_clip);
-                        const float4 lm = __ldg(reinterpret_cast<const float4*>(g.logmel + frame * (GN * 4) + n * 4));
-                        const float2* gg = reinterpret_cast<const float2*>(G + idx * 6);
-                        const float2 g0 = gg[0], g1 = gg[1], g2 = gg[2];
-                        float2* dst = reinterpret_cast<float2*>(g.feat + ((clip * g.t_out + t) * GN + n) * 10);
-                        dst[0] = make_float2(lm.x, lm.y);
-                        dst[1] = make_float2(lm.z, lm.w);
-                        dst[2] = g0;
-                        dst[3] = g1;
-                        dst[4] = g2;
-                    }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");          // G is rewritten by the next tile
+                for (int n = 0; n < GN; n += 4)
+                    d4[n / 4] = make_float4(__uint_as_float(v[n]) * g.scale, __uint_as_float(v[n + 1]) * g.scale,
+                                            __uint_as_float(v[n + 2]) * g.scale, __uint_as_float(v[n + 3]) * g.scale);
             }
         }
     }
@@ -244,12 +215,10 @@ __global__ void __launch_bounds__(192) gcc_gemm_kernel(GccGemmArgs g) {
 
 int launch_gcc_gemm(const GccGemmArgs& g, int num_sms, cudaStream_t st) {
     if (g.n_tiles <= 0) return SELD_OK;
-    const int smem = GSTAGES * GSTAGE_BYTES + GSTAGING_BYTES + 1024;      // 105 KB -> 2 CTAs per SM (128 TMEM columns each)
-    static std::atomic<int> configured{0};
-    if (!configured.load(std::memory_order_acquire)) {
+    const int smem = GSTAGES * GSTAGE_BYTES + 1024;      // 73 KB -> up to 3 CTAs per SM (128 TMEM columns each)
+    static unsigned long long configured = 0;             // bit d: attribute set on device d
+    if (first_use_on_device(&configured))
         SELD_CUDA_TRY(cudaFuncSetAttribute(gcc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured.store(1, std::memory_order_release);
-    }
     long long grid = (long long)num_sms * 2;
     if (grid > g.n_tiles) grid = g.n_tiles;
     gcc_gemm_kernel<<<(int)grid, 192, smem, st>>>(g);
@@ -271,15 +240,12 @@ extern "C" int seld_gcc_gemm(const void* a_img_dev, const void* bt_img_dev, int6
         set_error("operands must be 16-byte aligned");
         return SELD_EINVAL;
     }
-    static int checked = 0, sms = 148;          // one device query per process (it is slow and takes driver locks)
-    if (!checked) {
+    static unsigned long long checked = 0;      // one device check per device (the query is slow and takes driver locks)
+    if (first_use_on_device(&checked)) {
         const int rc = seld_device_check(-1);
         if (rc != SELD_OK) return rc;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        checked = 1;
     }
+    const int sms = device_sm_count();
     GccGemmArgs g{};
     g.A = static_cast<const __half*>(a_img_dev);
     g.Bt = static_cast<const __half*>(bt_img_dev);
@@ -287,10 +253,5 @@ extern "C" int seld_gcc_gemm(const void* a_img_dev, const void* bt_img_dev, int6
     g.scale = scale;
     g.dense_out = out_dev;
     g.dense_rows = rows;
-    g.feat = nullptr;
-    g.logmel = nullptr;
-    g.n_frames = 0;
-    g.frames_per_clip = 1;
-    g.t_out = 1;
     return launch_gcc_gemm(g, sms, static_cast<cudaStream_t>(stream));
 }

@@ -158,12 +158,7 @@ extern "C" int seld_mask(void* x_dev, int dtype, int64_t n_samples, int64_t t, i
     if (freq_n > 0 && freq_max > f) { set_error("freq max_mask_size exceeds the axis length"); return SELD_EINVAL; }
     if (rng_mode == SELD_RNG_TF_EAGER_COMPAT && op_seed2_dev == nullptr) { set_error("TF_EAGER_COMPAT needs op_seed2"); return SELD_EINVAL; }
     if (rng_mode != SELD_RNG_TF_EAGER_COMPAT && rng_mode != SELD_RNG_PHILOX_COUNTER) { set_error("bad rng_mode"); return SELD_EINVAL; }
-    static const int num_sms = [] {
-        int dev = 0, v = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        return v;
-    }();
+    const int num_sms = device_sm_count();
     MaskArgs a;
     a.x = x_dev;
     a.n_samples = n_samples; a.t = t; a.mid = mid; a.f = f; a.c = c;
@@ -231,7 +226,7 @@ extern "C" int seld_channel_remap(const float* in_dev, float* out_dev, int64_t n
     if (per_sample >= (1ll << 31) || n_samples > 65535) { set_error("sample too large (2^31 elements) or more than 65535 samples"); return SELD_EUNSUPPORTED; }
     if (per_sample == 0 || n_samples == 0) return SELD_OK;
     long long bx = (per_sample + 255) / 256;
-    const long long cap = (148ll * 16 + n_samples - 1) / n_samples;
+    const long long cap = ((long long)device_sm_count() * 16 + n_samples - 1) / n_samples;
     if (bx > cap) bx = cap < 1 ? 1 : cap;
     dim3 grid((unsigned)bx, (unsigned)n_samples);
     channel_remap_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_dev, out_dev, (unsigned)per_sample, (unsigned)n_chan,
@@ -268,7 +263,7 @@ extern "C" int seld_channel_offset(const float* in_dev, float* out_dev, int64_t 
     if (per_sample >= (1ll << 31) || n_samples > 65535) { set_error("sample too large (2^31 elements) or more than 65535 samples"); return SELD_EUNSUPPORTED; }
     if (per_sample == 0 || n_samples == 0) return SELD_OK;
     long long bx = (per_sample + 255) / 256;
-    const long long cap = (148ll * 16 + n_samples - 1) / n_samples;
+    const long long cap = ((long long)device_sm_count() * 16 + n_samples - 1) / n_samples;
     if (bx > cap) bx = cap < 1 ? 1 : cap;
     dim3 grid((unsigned)bx, (unsigned)n_samples);
     channel_offset_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_dev, out_dev, (unsigned)per_sample, (unsigned)n_chan,

@@ -39,6 +39,10 @@ struct seld_plan {
 namespace seld {
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
+// multiprocessor count of the CURRENT device, queried once per device (a process may drive several GPUs)
+int device_sm_count();
+// true the first time it is called for (slot, current device): "set this kernel attribute once per device"
+bool first_use_on_device(unsigned long long* slot_bits);
 }  // namespace seld
 
 #define SELD_CUDA_TRY(expr)                                          \

@@ -32,6 +32,13 @@ __device__ __forceinline__ float floor_of(const unsigned int* __restrict__ keys,
     return (keys != nullptr && c.t < t_valid) ? key_to_float(__ldg(keys + c.clip)) - top_db : -INFINITY;
 }
 
+// torch.max(db, floor): NaN in either operand gives NaN (fmaxf alone would drop it) -- a clip with a NaN sample has a NaN
+// maximum, hence a NaN floor, hence NaN log-mel everywhere, as in the reference (feature_extractor.py:65-71)
+__device__ __forceinline__ float clamp_db(float x, float fl) {
+    const float r = fmaxf(x, fl);
+    return (x != x || fl != fl) ? NAN : r;
+}
+
 // ------------------------------------------------------------------ finalize (vector path: row_len % 4 == 0)
 __global__ void __launch_bounds__(512) finalize_rows_kernel(const float* __restrict__ in, const unsigned int* __restrict__ keys,
                                                             long long n_rows, int t_out, int t_valid, int row_len, int n_ch,
@@ -70,7 +77,7 @@ __global__ void __launch_bounds__(512) finalize_rows_kernel(const float* __restr
             float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (logmel[j]) x[j] = fmaxf(x[j], fl[u]);
+                if (logmel[j]) x[j] = clamp_db(x[j], fl[u]);
                 x[j] = (x[j] - m[j]) * inv[j];
             }
             __stcs(dst + base + u * stride4, make_float4(x[0], x[1], x[2], x[3]));
@@ -83,7 +90,7 @@ __global__ void __launch_bounds__(512) finalize_rows_kernel(const float* __restr
         float x[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (logmel[j]) x[j] = fmaxf(x[j], fl);
+            if (logmel[j]) x[j] = clamp_db(x[j], fl);
             x[j] = (x[j] - m[j]) * inv[j];
         }
         __stcs(dst + r * g4 + g, make_float4(x[0], x[1], x[2], x[3]));
@@ -100,7 +107,7 @@ __global__ void __launch_bounds__(256) finalize_scalar_kernel(const float* __res
         const long long row = e / row_len;
         const int p = int(e - row * row_len);
         float v = in[e];
-        if ((p % n_ch) < 4 && keys != nullptr && int(row % t_out) < t_valid) v = fmaxf(v, key_to_float(keys[row / t_out]) - top_db);
+        if ((p % n_ch) < 4 && keys != nullptr && int(row % t_out) < t_valid) v = clamp_db(v, key_to_float(keys[row / t_out]) - top_db);
         if (mean != nullptr) v = (v - mean[p]) * (1.0f / fmaxf(stdv[p], eps));
         out[e] = v;
     }
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(512) stats_partial_kernel(const float* __restr
         float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (logmel[j]) v[j] = fmaxf(v[j], fl);
+            if (logmel[j]) v[j] = clamp_db(v[j], fl);
             const double d = double(v[j]);
             s[j] += d;
             q[j] = fma(d, d, q[j]);
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(256) stats_partial_scalar_kernel(const float* 
         double s = 0, q = 0;
         for (long long r = r0; r < r1; ++r) {
             float v = x[r * row_len + p];
-            if (logmel && keys != nullptr && int(r % t_out) < t_valid) v = fmaxf(v, key_to_float(keys[r / t_out]) - top_db);
+            if (logmel && keys != nullptr && int(r % t_out) < t_valid) v = clamp_db(v, key_to_float(keys[r / t_out]) - top_db);
             s += double(v);
             q = fma(double(v), double(v), q);
         }
@@ -219,15 +226,7 @@ using namespace seld;
 
 extern "C" {
 
-static int sm_count() {          // one cheap attribute query per process (every rank drives one device)
-    static const int n = [] {
-        int dev = 0, v = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        return v;
-    }();
-    return n;
-}
+static int sm_count() { return device_sm_count(); }
 static int stats_block_count() { return sm_count() * 4; }
 
 int seld_finalize(int n_mels, int n_ch, const float* feat_in_dev, const uint32_t* clip_max_key_dev, int n_clips, int t_out,

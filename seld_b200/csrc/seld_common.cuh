@@ -117,6 +117,7 @@ SELD_HD uint32_t float_to_key(float f) {
 #endif
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+constexpr uint32_t kNanKey = 0xFFC00000u;      // key of +NaN: above every finite value and +inf (a NaN clip maximum poisons the clip)
 SELD_HD float key_to_float(uint32_t k) {
     uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
 #if defined(__CUDA_ARCH__)

@@ -152,7 +152,7 @@ int seld_foa_iv(const float* spec_dev, int64_t n, float eps, float* iv_dev, void
     if (!spec_dev || !iv_dev || n < 0) { set_error("bad argument"); return SELD_EINVAL; }
     if (n == 0) return SELD_OK;
     long long blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
     foa_iv_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float2*>(spec_dev), n, eps,
                                                                               iv_dev);
     SELD_CUDA_TRY(cudaGetLastError());

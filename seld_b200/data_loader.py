@@ -48,12 +48,14 @@ class _BatchIterable:
     def __init__(self, xs, ys, n_samples, batch_size, loop_time, sample_transforms, batch_transforms, shuffle_size, seed):
         self.xs, self.ys, self.n = xs, ys, int(n_samples)
         self.batch_size = int(batch_size)
-        self.loop_time = 1 if loop_time is None else int(loop_time)
+        self.loop_time = None if loop_time is None else int(loop_time)      # None: repeat for ever (dataset.repeat(None), :49)
         self.sample_transforms, self.batch_transforms = sample_transforms, batch_transforms
         self.shuffle_size = shuffle_size
         self.rng = np.random.default_rng(seed)
 
     def __len__(self):
+        if self.loop_time is None:
+            raise TypeError('an endlessly repeating loader (loop_time=None) has no length')
         return -(-self.n * self.loop_time // self.batch_size)
 
     def batch_order(self):
@@ -77,20 +79,38 @@ class _BatchIterable:
         return out
 
     def _slice(self, lo, hi):
-        """Samples [lo, hi) of the repeated stream (contiguous views where the range does not wrap)."""
+        """Samples [lo, hi) of the repeated stream: a contiguous view where the range stays inside one pass, two views
+        joined where it wraps once, a modular gather where a batch spans several passes (batch_size > n)."""
         lo_m, hi_m = lo % self.n, (hi - 1) % self.n + 1
-        if lo // self.n == (hi - 1) // self.n:
+        wraps = (hi - 1) // self.n - lo // self.n
+        if wraps == 0:
             return self.xs[lo_m:hi_m], self.ys[lo_m:hi_m]
-        return (torch.cat([self.xs[lo_m:], self.xs[:hi_m]]), torch.cat([self.ys[lo_m:], self.ys[:hi_m]]))
+        if wraps == 1:
+            return (torch.cat([self.xs[lo_m:], self.xs[:hi_m]]), torch.cat([self.ys[lo_m:], self.ys[:hi_m]]))
+        idx = torch.arange(lo, hi, device=self.xs.device) % self.n
+        return self.xs.index_select(0, idx), self.ys.index_select(0, idx.to(self.ys.device))
+
+    def _batch(self, lo, hi):
+        x, y = self._slice(lo, hi)
+        x, y = _apply(self.sample_transforms, x, y, per_sample=True)
+        return _apply(self.batch_transforms, x, y, per_sample=False)
 
     def __iter__(self):
+        if self.loop_time is None:                      # endless: batches in stream order, shuffled buffer-wise on the fly
+            if self.n == 0:
+                return
+            buf, b = [], 0
+            size = self.shuffle_size if self.shuffle_size and self.shuffle_size > 1 else 1
+            while True:
+                while len(buf) < size:
+                    buf.append(b)
+                    b += 1
+                i = int(self.rng.integers(len(buf))) if size > 1 else 0
+                nxt = buf.pop(i)
+                yield self._batch(nxt * self.batch_size, (nxt + 1) * self.batch_size)
         total = self.n * self.loop_time
         for b in self.batch_order():
-            lo, hi = b * self.batch_size, min((b + 1) * self.batch_size, total)
-            x, y = self._slice(lo, hi)
-            x, y = _apply(self.sample_transforms, x, y, per_sample=True)
-            x, y = _apply(self.batch_transforms, x, y, per_sample=False)
-            yield x, y
+            yield self._batch(b * self.batch_size, min((b + 1) * self.batch_size, total))
 
 
 def data_loader(dataset, preprocessing=None, sample_transforms=None, batch_transforms=None, deterministic=False,
@@ -144,14 +164,18 @@ def get_preprocessed_x(wav, sample_rate, mode='foa', n_mels=64, multiplier=5, ma
     ``wav [4, L]`` (or a batch ``[n, 4, L]``), top_db-clamped, zero-padded / truncated to ``max_label_length * multiplier``
     frames -> CUDA float32 ``[max_len, n_mels, C]`` (``[n, max_len, n_mels, C]`` for a batch).  One fused launch + the clamp;
     the reference's numpy-or-tensor return type becomes a device tensor."""
-    from . import pipeline
+    from . import _lib, pipeline
+    from .plan import get_plan
+    _lib.require_device()
     w = torch.as_tensor(wav)
     single = w.dim() == 2
-    w = (w.unsqueeze(0) if single else w).to(device='cuda', dtype=torch.float32).contiguous()
+    dev = w.device if w.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    w = (w.unsqueeze(0) if single else w).to(device=dev, dtype=torch.float32).contiguous()
     max_len = int(max_label_length) * int(multiplier)
     feat, key = pipeline.extract_batch(w, sample_rate, mode=mode, n_mels=n_mels, t_out=max_len, **kwargs)
-    hop = kwargs.get('hop_length') or (kwargs.get('win_length') or kwargs.get('n_fft', 512)) // 2
-    pipeline.finalize_(feat, key, 1 + w.shape[-1] // hop)
+    with torch.cuda.device(w.device):
+        plan = get_plan(sample_rate, mode=mode, n_mels=n_mels, **{k: v for k, v in kwargs.items() if k != 'pad'})
+    pipeline.finalize_(feat, key, plan.num_frames(w.shape[-1] + 2 * int(kwargs.get('pad', 0))))
     return feat[0] if single else feat
 
 

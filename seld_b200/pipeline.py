@@ -24,22 +24,8 @@ def _check_cuda_f32(t, name):
         raise ValueError(f'{name} must be a contiguous float32 CUDA tensor')
 
 
-_workspaces = {}
-
-
-def _workspace(device, n_bytes):
-    """Per-device scratch for the tensor-core GCC path, grown on demand (stream-ordered reuse: every use is enqueued
-    on the current stream before the next one)."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    buf = _workspaces.get(key)
-    if buf is None or buf.numel() < n_bytes:
-        _workspaces[key] = buf = torch.empty(n_bytes, dtype=torch.uint8, device=device)
-    return buf
-
-
 def release_workspaces():
-    """Drop the cached GCC scratch buffers (22 GB for a 600-clip MIC shard)."""
-    _workspaces.clear()
+    """Kept for callers of round-1 code: the tensor-core GCC path is fused into the extractor and needs no scratch."""
 
 
 def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', out=None, key=None,
@@ -49,6 +35,8 @@ def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='p
 
     Returns (feat_raw [n_clips, t_out, n_mels, C] float32, clip_max_key [n_clips] int32 keys).  Log-mel channels
     are NOT yet clamped to clip_max - 80 dB: pass both to finalize_ / partial_statistics.
+    MIC at n_fft 1024 / 64 mels runs the GCC lag projection on the tensor cores inside the same kernel;
+    ``use_tensor_cores=False`` selects the CUDA-core inverse transforms instead (tests compare the two).
     Replaces reference feature_extractor.py:53-88 + :140-147 for a batch of clips.
     """
     pcm16 = isinstance(wav, torch.Tensor) and wav.dtype == torch.int16
@@ -97,17 +85,13 @@ def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='p
         if key is None:
             key = torch.empty(n_clips, dtype=torch.int32, device=wav.device)
         lib = _lib.load()
-        ws, ws_bytes = None, 0
-        if use_tensor_cores and center:
-            ws_bytes = int(lib.seld_extract_workspace_bytes(plan.handle, n_clips, n_samples, int(t_out)))
-            if ws_bytes > 0:
-                ws = _workspace(wav.device, ws_bytes)
+        ws, ws_bytes = None, (0 if use_tensor_cores else -1)       # no scratch any more; < 0 = "CUDA-core GCC"
         if pcm16:
             _lib.check(lib.seld_extract_pcm16(plan.handle, _lib.ptr(wav), n_clips, n_samples, int(t_out),
                                               _lib.ptr(out), _lib.ptr(key), _lib.ptr(ws), ws_bytes, _lib.current_stream_ptr()))
         elif not center:
             _lib.check(lib.seld_extract_chunks(plan.handle, _lib.ptr(wav), code, n_clips, n_samples, int(t_out),
-                                               _lib.ptr(out), _lib.ptr(key), None, 0, _lib.current_stream_ptr()))
+                                               _lib.ptr(out), _lib.ptr(key), None, ws_bytes, _lib.current_stream_ptr()))
         else:
             _lib.check(lib.seld_extract(plan.handle, _lib.ptr(wav), code, n_clips, n_samples, int(t_out),
                                         _lib.ptr(out), _lib.ptr(key), _lib.ptr(ws), ws_bytes, _lib.current_stream_ptr()))

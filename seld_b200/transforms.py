@@ -215,12 +215,20 @@ def sample_masks(time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, le
     ``mask(x, axis=-2, max_mask_size=16)``; trainv2.py:134-138 puts ``random_ups_and_downs`` in front: ``level_jitter=0.2``)
     as ONE batched transform for ``data_loader.seldnet_data_to_dataloader``: ``(x [B, T, F, C], y) -> (new x, y)``,
     independent draws per sample; the level jitter rides on the copy the masks need, then one fused masking launch."""
+    state = {'next_sample': 0}          # with an explicit seed: this transform's own running sample index, so that every
+    lock = threading.Lock()             # batch (and every epoch) draws fresh bands, reproducibly
+
     def op(x, y):
+        first = None
+        if seed is not None:
+            with lock:
+                first = state['next_sample']
+                state['next_sample'] += int(x.shape[0])
         if level_jitter:
-            out = _offset_copy(x, _level_offsets(x.shape[0], float(level_jitter), seed, None), min(4, x.shape[-1]))
+            out = _offset_copy(x, _level_offsets(x.shape[0], float(level_jitter), seed, first), min(4, x.shape[-1]))
         else:
             out = x.clone(memory_format=torch.contiguous_format)
-        mask_batch_(out, time_mask, freq_mask, period=period, seed=seed)
+        mask_batch_(out, time_mask, freq_mask, period=period, seed=seed, sample_offset=first)
         return out, y
     op.batched = True
     return op

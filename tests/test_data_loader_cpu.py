@@ -11,11 +11,31 @@ def test_data_loader_shapes_like_reference_test():
     xs, ys = torch.arange(data_size), torch.arange(data_size, 0, -1)
     ident = [lambda x, y: (x, y)]
     seen = 0
-    for x, y in DL.data_loader((xs, ys), sample_transforms=ident, batch_transforms=ident, batch_size=batch_size):
+    for x, y in DL.data_loader((xs, ys), sample_transforms=ident, batch_transforms=ident, batch_size=batch_size, loop_time=1):
         assert tuple(x.shape) == (batch_size,) and tuple(y.shape) == (batch_size,)
         assert torch.equal(x + y, torch.full((batch_size,), data_size))
         seen += 1
     assert seen == 2
+
+
+def test_default_loop_time_repeats_for_ever_like_dataset_repeat_none():
+    """reference data_loader.py:17,51: loop_time=None is `dataset.repeat(None)` -- an endless stream (the reference's own
+    test iterates it with a `for`, which only ends because nobody waits for it)."""
+    import itertools
+    import pytest
+    xs, ys = torch.arange(5), torch.arange(5, 0, -1)
+    dl = DL.data_loader((xs, ys), batch_size=4)
+    got = torch.cat([x for x, _ in itertools.islice(dl, 7)])
+    assert torch.equal(got, torch.arange(28) % 5)                   # batches straddle the passes, nothing is dropped
+    with pytest.raises(TypeError):
+        len(dl)
+
+
+def test_batches_larger_than_the_dataset_wrap_several_times():
+    xs, ys = torch.arange(3), torch.arange(3)
+    batches = [x for x, _ in DL.data_loader((xs, ys), batch_size=8, loop_time=4)]
+    assert [len(b) for b in batches] == [8, 4]
+    assert torch.equal(torch.cat(batches), torch.arange(12) % 3)
 
 
 def test_seldnet_data_to_dataloader_shapes_like_reference_test():
@@ -99,7 +119,7 @@ def test_per_sample_transforms_are_mapped_and_batched_ones_get_the_batch():
         return x * 2, y
     batched.batched = True
     xs, ys = torch.zeros(4, 3), torch.zeros(4)
-    out = list(DL.data_loader((xs, ys), sample_transforms=[per_sample, batched], batch_size=4))
+    out = list(DL.data_loader((xs, ys), sample_transforms=[per_sample, batched], batch_size=4, loop_time=1))
     assert calls == [(3,)] * 4 + [('batch', 4, 3)]
     assert torch.equal(out[0][0], torch.full((4, 3), 2.0))
 

@@ -92,3 +92,22 @@ def test_sample_masks_with_level_jitter():
         hi = (out[b] - x[b])[..., 4:][keep[..., 4:]]
         assert float(hi.abs().max()) == 0.0
         assert float(lo.max() - lo.min()) < 1e-6
+
+
+def test_seeded_sample_masks_draw_fresh_bands_every_batch():
+    """With an explicit seed the transform keeps its own running sample index: consecutive batches (and epochs) get
+    different bands and jitter, and a second transform with the same seed reproduces the sequence."""
+    x = (torch.rand(8, 300, 64, 7) + 1.0).cuda()
+    runs = []
+    for _ in range(2):
+        op = T.sample_masks(time_mask=(24, 1), freq_mask=(16, 1), seed=1, level_jitter=0.2)
+        runs.append([op(x, None)[0] for _ in range(3)])
+    a, b, c = runs[0]
+    assert not torch.equal(a == 0, b == 0) and not torch.equal(b == 0, c == 0)
+    assert not torch.equal(a[..., :4][(a != 0)[..., :4]][:100], b[..., :4][(b != 0)[..., :4]][:100])
+    for first, second in zip(*runs):
+        assert torch.equal(first, second)
+    # batch k of the transform == one call on samples [8k, 8k + 8) of the stream
+    want = x.clone()
+    T.mask_batch_(want, (24, 1), (16, 1), seed=1, sample_offset=8)
+    assert torch.equal((want == 0), (b == 0))
