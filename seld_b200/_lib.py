@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libseld_b200.so')
+LIB_PATH = os.environ.get('SELD_B200_LIB') or os.path.join(_HERE, 'libseld_b200.so')      # (override: kernel experiments only)
 
 MODE_FOA, MODE_MIC = 0, 1
 LAYOUT_PLANAR_CL, LAYOUT_INTERLEAVED_LC = 0, 1

@@ -90,6 +90,10 @@ static int frames_per_team(int dflt) {   // consecutive frames a team handles pe
 }
 
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
+#ifndef SELD_GCC_DEAD
+#define SELD_GCC_DEAD 1
+#endif
+constexpr bool kGccDead = SELD_GCC_DEAD;               // (experiments: cost of the dead-channel detection)
 constexpr int kGccTileBytes = GT_BYTES;          // fused GCC: phasor tile (the exchange buffers alias it) ...
 constexpr int kGccNyqBytes = GT_NYQ_BYTES + 16;  // ... + the Nyquist column + the dead-channel flags of the two warps
 
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     }
     if constexpr (FUSED) {
         if (threadIdx.x < 8) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&s_mbar[threadIdx.x])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_addr(&s_mbar[threadIdx.x])));      // one commit per warp of the team
             asm volatile("fence.mbarrier_init.release.cluster;");
         }
     }
@@ -276,6 +280,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     const int pteam = team ^ 1;
     float* acc_part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(acc) + (pteam - team) * team_stride);
     unsigned par_mine = 0, par_part = 0;
+    const unsigned tmem_base = taddr - ((32u * (warp & 3)) << 16);
     volatile unsigned* dead_flags = reinterpret_cast<volatile unsigned*>(nyq + GT_NYQ_BYTES);     // [2]: bits (channel 2h, 2h + 1) of warp h
 
     // forward FFT stage 2 of this warp; the fused kernel lays the spectrum out as the MMA's B tile (both warps' rows
@@ -293,13 +298,28 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     // fused GCC: is a channel of this warp's pair exactly zero over the whole windowed frame?  (the reference's phase
     // transform of a dead microphone is a sign pattern of the live partner, extract_core.cuh: dead_pair)
     auto note_dead = [&](const float2* v) {
-        if constexpr (FUSED) {
+        if constexpr (FUSED && kGccDead) {
             unsigned ox = 0, oy = 0;
 #pragma unroll
             for (int n2 = 0; n2 < R; ++n2) { ox |= __float_as_uint(v[n2].x); oy |= __float_as_uint(v[n2].y); }
             const unsigned dx = __all_sync(0xffffffffu, (ox << 1) == 0), dy = __all_sync(0xffffffffu, (oy << 1) == 0);
             if (lane == 0) dead_flags[h] = dx | (dy << 1);
         }
+    };
+
+    // running clip maximum of this warp; a NaN log-mel value makes it NaN (reference: db.max(), feature_extractor.py:65-71)
+    auto note_max = [&](int clip, float mx) {
+        const bool nan_any = __any_sync(0xffffffffu, mx != mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (clip != run_clip) {
+            if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], run_nan ? kNanKey : float_to_key(run_max));
+            run_clip = clip;
+            run_max = -INFINITY;
+            run_nan = false;
+        }
+        run_max = fmaxf(run_max, mx);
+        run_nan = run_nan || nan_any;
     };
 
     // everything after the team's two packed FFTs: mel pieces, gather, GCC, row store, running clip maximum.
@@ -309,16 +329,14 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         if constexpr (FUSED) {
             if (mine) {
                 team_bar(bar_id);                                        // both spectra are in the tile
-                const unsigned dead = dead_flags[0] | (dead_flags[1] << 2);
+                const unsigned dead = kGccDead ? (dead_flags[0] | (dead_flags[1] << 2)) : 0u;
                 if (dead) bin_phase_gcc_fused<true>(tile, nyq, tb, X, u, taddr + TMEM_COL_W01, dead);
                 else bin_phase_gcc_fused<false>(tile, nyq, tb, X, u, taddr + TMEM_COL_W01, 0u);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the phasor rows -> visible to the tensor core
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 team_bar(bar_id);
-                if (h == 0) {
-                    if (elect_one()) gcc_issue_mma(smem_addr(tile), taddr - ((32u * (warp & 3)) << 16), team, smem_addr(&s_mbar[team]));
-                    __syncwarp();
-                }
+                if (elect_one()) gcc_issue_mma(smem_addr(tile), tmem_base, gcc_dcol(team, 0), smem_addr(&s_mbar[team]), h);
+                __syncwarp();
                 mx = gather_lanes<MODE>(X, tb, acc, a.n_mels, u);       // log-mel while the MMAs run
                 mbar_wait_parity(smem_addr(&s_mbar[team]), par_mine);
                 par_mine ^= 1u;
@@ -328,8 +346,8 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                 par_part ^= 1u;
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (mine) gcc_epilogue(taddr, team, warp & 3, lane, acc);
-            if (part) gcc_epilogue(taddr, pteam, warp & 3, lane, acc_part);
+            if (mine) gcc_epilogue(taddr, gcc_dcol(team, 0), warp & 3, lane, acc);
+            if (part) gcc_epilogue(taddr, gcc_dcol(pteam, 0), warp & 3, lane, acc_part);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             pair_bar(9 + (team >> 1));                                   // both rows are complete; both accumulators are free
             if (!mine) return;
@@ -361,18 +379,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         // (an asynchronous bulk store of the row -- fence.proxy.async + cp.async.bulk shared -> global by one lane -- measured
         //  no faster than these 128-bit copies: 9.99 vs 9.93 ms)
         if (row != nullptr) store_row(acc, row_elems, row, u, TL);
-        // a NaN log-mel value makes the clip maximum NaN (reference: db.max(), feature_extractor.py:65-71)
-        const bool nan_any = __any_sync(0xffffffffu, mx != mx);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (clip != run_clip) {
-            if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], run_nan ? kNanKey : float_to_key(run_max));
-            run_clip = clip;
-            run_max = -INFINITY;
-            run_nan = false;
-        }
-        run_max = fmaxf(run_max, mx);
-        run_nan = run_nan || nan_any;
+        note_max(clip, mx);
     };
 
     if constexpr (EDGE) {
@@ -482,17 +489,22 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         int prev_clip = -1, prev_t = -2;
         // (prefetching just the 15 new taps of the next frame in 30 registers was tried on top of this: 104 B of spills and
         //  9.58 ms instead of 9.06)
+        // (Fused GCC: deferring a frame's epilogue into the next iteration -- accumulators and staged rows double-buffered, the
+        //  MMAs running under the next frame's FFTs -- was built and measured: 18.5 ms per 600 clips against 17.3 for waiting
+        //  right after the gather; the tensor pipe is 9 % busy, the wait is not what this kernel is short of.)
 #pragma unroll 1
         while (g >= 0 || gpart >= 0) {
             const bool mine = g >= 0;
             if (++fi == a.fpw) { fi = 0; sc += sc_step; }
             const long long g_next = frame_index(sc, fi, team);
             const long long gpart_next = FUSED ? frame_index(sc, fi, pteam) : -1;
-            if (!mine) {                                  // (fused GCC) only the partner has a frame left: help read its accumulator
-                finish_frame(false, true, 0, 0, nullptr);
-                g = g_next;
-                gpart = gpart_next;
-                continue;
+            if constexpr (FUSED) {
+                if (!mine) {                              // only the partner has a frame: help read its accumulator
+                    finish_frame(false, true, 0, 0, nullptr);
+                    g = g_next;
+                    gpart = gpart_next;
+                    continue;
+                }
             }
             if constexpr (!PREFETCH) {
                 if constexpr (KEEP) {
@@ -546,15 +558,17 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                 if constexpr (LAYOUT == LAYOUT_PCM16_LC) apply_window_pcm16<R, 32>(raw, 0, wlane, v);
                 else apply_window<R, 32>(raw, wlane, v);
             }
-            note_dead(v);
             const int clip_now = clip, t_now = t;
             float* row = (t < a.t_out) ? a.out + ((long long)clip * a.t_out + t) * row_elems : nullptr;
             if (PREFETCH && g_next >= 0) request(g_next);
-            if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
-            else stage1_fft_store<R>(v, tb, E, lane);
-            __syncwarp();
-            stage2();
-            finish_frame(true, gpart >= 0, clip_now, t_now, row);
+            {
+                note_dead(v);
+                if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
+                else stage1_fft_store<R>(v, tb, E, lane);
+                __syncwarp();
+                stage2();
+                finish_frame(true, gpart >= 0, clip_now, t_now, row);
+            }
             g = g_next;
             gpart = gpart_next;
         }

@@ -29,6 +29,7 @@
 #include "mel_pieces.h"
 #if defined(__CUDACC__)
 #include <cuda_fp16.h>
+#include <type_traits>
 #endif
 
 namespace seld {
@@ -307,10 +308,9 @@ __device__ __forceinline__ void tmem_st16(unsigned taddr, const float* r) {
 
 // stage1_fft_store with the twiddles read from tensor memory (same values, same arithmetic as the shared-table version)
 template <int R>
-__device__ __forceinline__ void stage1_fft_store_tm(float2* v, unsigned taddr_tw, float2* E, int lane) {
+__device__ __forceinline__ void stage1_store_tm(const float2* v, unsigned taddr_tw, float2* E, int lane) {   // v: pfft_dif output
     using G = Geo<R>;
     static_assert(R % 8 == 0, "twiddles are fetched 8 at a time");
-    pfft_dif<R>(v);
     float4* E4 = reinterpret_cast<float4*>(E + lane * G::EP);
 #pragma unroll
     for (int g = 0; g < R / 8; ++g) {
@@ -325,6 +325,11 @@ __device__ __forceinline__ void stage1_fft_store_tm(float2* v, unsigned taddr_tw
             E4[j] = q;
         }
     }
+}
+template <int R>
+__device__ __forceinline__ void stage1_fft_store_tm(float2* v, unsigned taddr_tw, float2* E, int lane) {
+    pfft_dif<R>(v);
+    stage1_store_tm<R>(v, taddr_tw, E, lane);
 }
 #endif
 
@@ -676,7 +681,8 @@ constexpr int GT_UNIT = 144;                    // byte pitch of a 16-byte K uni
 constexpr int GT_CHUNK = 8 * GT_UNIT;           // 32 bins
 constexpr int GT_BYTES = 128 * GT_UNIT;         // 512 bins: 18 432 bytes (the two exchange buffers alias its first 17 408)
 constexpr int GT_NYQ_BYTES = 128;               // Nyquist "column": rows 0, 1 = Z0[512], rows 4, 5 = Z1[512]
-constexpr int TMEM_COL_BASIS = 128, TMEM_COL_D = 384;
+constexpr int TMEM_COL_BASIS = 128, TMEM_COL_D = 384;         // D of team t: columns TMEM_COL_D + 8 t .. + 7
+__device__ __forceinline__ int gcc_dcol(int team, int) { return TMEM_COL_D + 8 * team; }
 
 __device__ __forceinline__ bool elect_one() {   // one lane of a converged warp (lets ptxas issue UTCHMMA without a per-thread loop)
     unsigned pred;
@@ -701,6 +707,11 @@ __device__ __forceinline__ void stage2_store_tile(const float2* u, unsigned char
 
 // six pair phasors conj(u_m) u_n of the per-channel unit phasors u_c = X_c / |X_c| (one MUFU.RSQ per channel on the power the
 // log-mel block needs anyway); a pair with a zero channel is 1, as exp(i angle(0)) = 1.  Pair order: reference :207-208.
+// A zero (underflowing) bin in a live frame is rare: the fix-up selects sit behind a warp vote.
+#ifndef SELD_GCC_VOTE_ZERO
+#define SELD_GCC_VOTE_ZERO 1
+#endif
+template <bool VOTE>      // VOTE: called by the whole (converged) warp
 __device__ __forceinline__ void pair_phasors(const float2* ch, const float* val, float2* p) {
     float2 uc[4];
     bool zc[4];
@@ -710,12 +721,18 @@ __device__ __forceinline__ void pair_phasors(const float2* ch, const float* val,
         const float inv = rsqrt_ftz(val[c]);
         uc[c] = pmul(ch[c], make_float2(inv, inv));
     }
-    p[0] = unit_pair(uc[0], uc[1], zc[0] || zc[1]);
-    p[1] = unit_pair(uc[0], uc[2], zc[0] || zc[2]);
-    p[2] = unit_pair(uc[0], uc[3], zc[0] || zc[3]);
-    p[3] = unit_pair(uc[1], uc[2], zc[1] || zc[2]);
-    p[4] = unit_pair(uc[1], uc[3], zc[1] || zc[3]);
-    p[5] = unit_pair(uc[2], uc[3], zc[2] || zc[3]);
+    constexpr int PM[6] = {0, 0, 0, 1, 1, 2}, PN[6] = {1, 2, 3, 2, 3, 3};
+    if constexpr (VOTE && SELD_GCC_VOTE_ZERO) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) p[q] = unit_pair(uc[PM[q]], uc[PN[q]], false);
+        if (__any_sync(0xffffffffu, zc[0] || zc[1] || zc[2] || zc[3])) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) if (zc[PM[q]] || zc[PN[q]]) p[q] = make_float2(1.f, 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) p[q] = unit_pair(uc[PM[q]], uc[PN[q]], zc[PM[q]] || zc[PN[q]]);
+    }
 }
 
 // The reference on a DEAD channel (an exactly zero spectrum): R = conj(X_m) X_n is a signed zero, torch.angle gives pi where
@@ -758,8 +775,8 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
 #pragma unroll
         for (int c = 0; c < 4; ++c) val[c] = fmaf(ch[c].x, ch[c].x, ch[c].y * ch[c].y);
     };
-    auto phasors = [&](const float2* ch, const float* val, float2* p) {
-        pair_phasors(ch, val, p);
+    auto phasors = [&](const float2* ch, const float* val, float2* p, auto vote) {
+        pair_phasors<decltype(vote)::value>(ch, val, p);
         if constexpr (DEAD) {
             constexpr int PM[6] = {0, 0, 0, 1, 1, 2}, PN[6] = {1, 2, 3, 2, 3, 3};
 #pragma unroll
@@ -768,21 +785,20 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
     };
     auto step = [&](int i, bool first, bool last) {
         const int k = kbeg + i;
-        const bool valid = k <= N / 2;
         // bins past N/2 (lanes 57 .. 63) carry zero weights and never close a piece: they read the Nyquist column
         const unsigned char* col = (k >= N / 2) ? nyq : tile + 36 * k - 32 * (k & 3);
         float2 ch[4];
         float val[NV];
         spectra(col, (first && k == 0) || (last && k >= N / 2), ch, val);
-        if (valid && k < N / 2) {
-            float2 p[6];
-            phasors(ch, val, p);
+        float2 p[6];
+        phasors(ch, val, p, std::true_type{});           // every lane (the zero fix-up votes); lanes past N/2 compute and drop
+        if (k < N / 2) {
             float w[6];
             if (first && k == 0) {                       // lane 0: the DC and Nyquist bins are real and share word 0 of each row
                 float2 chn[4], pn[6];
                 float valn[NV];
                 spectra(nyq, true, chn, valn);
-                phasors(chn, valn, pn);
+                phasors(chn, valn, pn, std::false_type{});
 #pragma unroll
                 for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, pn[q].x);
             } else {
@@ -817,22 +833,22 @@ __device__ __forceinline__ void mma_f16_ts(unsigned d_tmem, unsigned a_tmem, uns
                  :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// Issued by ONE elected thread once the team's phasor rows are in place (and fenced to the async proxy): 32 MMAs of
-// K = 16 per atom; tcgen05.commit arrives on the team's mbarrier when all of them have read the tile and written D.
-__device__ __forceinline__ void gcc_issue_mma(unsigned tile_saddr, unsigned tmem_base, int team, unsigned mbar_saddr) {
+// Issued by an elected thread of EACH warp of the team once the phasor rows are in place (and fenced to the async proxy):
+// warp h issues the 32 MMAs (K = 16 each) of atom h -- K half h of the basis, datapath lanes 16 h .. 16 h + 15 -- and
+// tcgen05.commit arrives on the team's mbarrier (count 2) when they have read the tile and written D.  (One thread issuing
+// all 64 held its warp ~600 cycles behind its partner at the next team barrier.)
+__device__ __forceinline__ void gcc_issue_mma(unsigned tile_saddr, unsigned tmem_base, int dcol, unsigned mbar_saddr, int half) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     constexpr unsigned idesc = (1u << 4) | ((8u >> 3) << 17) | ((64u >> 4) << 24);        // F32 accumulate, F16 x F16, K-major, N = 8, M = 64
     // no-swizzle K-major descriptor (cute::UMMA::SmemDescriptor): start address, LBO = 144 (K-adjacent core matrices),
     // SBO (8-row groups; a single group here), version 1
     const unsigned long long desc = (unsigned long long)((tile_saddr >> 4) & 0x3FFF) | ((unsigned long long)(GT_UNIT >> 4) << 16) |
                                     ((unsigned long long)(GT_CHUNK >> 4) << 32) | (1ull << 46);
-    const unsigned d_lo = tmem_base + TMEM_COL_D + 8 * team, a_lo = tmem_base + TMEM_COL_BASIS;
-    const unsigned up = 16u << 16;
+    const unsigned up = unsigned(half) * (16u << 16);
+    const unsigned d = tmem_base + dcol + up, a = tmem_base + TMEM_COL_BASIS + up;
+    const unsigned long long desc_h = desc + (unsigned long long)(unsigned(half) * ((2 * GT_UNIT * 32) >> 4));
 #pragma unroll
-    for (int s = 0; s < 32; ++s) {
-        mma_f16_ts(d_lo, a_lo + 8 * s, desc + (unsigned long long)((2 * GT_UNIT * s) >> 4), idesc, s > 0);
-        mma_f16_ts(d_lo + up, a_lo + up + 8 * s, desc + (unsigned long long)((2 * GT_UNIT * (32 + s)) >> 4), idesc, s > 0);
-    }
+    for (int s = 0; s < 32; ++s) mma_f16_ts(d, a + 8 * s, desc_h + (unsigned long long)((2 * GT_UNIT * s) >> 4), idesc, s > 0);
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar_saddr) : "memory");
 }
 
@@ -847,11 +863,11 @@ __device__ __forceinline__ void mbar_wait_parity(unsigned bar_saddr, unsigned pa
 // Epilogue of one team's accumulator, executed by every warp of the team PAIR (four warps = the four TMEM subpartitions):
 // warp quadrant q holds lags 16 q .. 16 q + 15 -- K < 512 partial sums in lanes 0..15, K >= 512 in lanes 16..31.  The six
 // GCC channels of a lag are 24 contiguous bytes of the staged feature row.
-__device__ __forceinline__ void gcc_epilogue(unsigned taddr_quadrant, int team, int q, int lane, float* acc_row) {
+__device__ __forceinline__ void gcc_epilogue(unsigned taddr_quadrant, int dcol, int q, int lane, float* acc_row) {
     float v[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "r"(taddr_quadrant + TMEM_COL_D + 8 * team) : "memory");
+                 : "r"(taddr_quadrant + dcol) : "memory");
 #pragma unroll
     for (int n = 0; n < 6; ++n) v[n] = (v[n] + __shfl_xor_sync(0xffffffffu, v[n], 16)) * (1.0f / 512.0f);     // the basis is stored x512
     if (lane < 16) {
