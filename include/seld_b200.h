@@ -58,6 +58,8 @@ typedef struct seld_plan* seld_plan_t;
 
 SELD_API const char* seld_last_error(void);
 SELD_API int seld_version(void);
+/* Kernels this library has launched in this process so far (all streams; what bench.py reports as gpu_launches). */
+SELD_API int64_t seld_launch_count(void);
 
 /* 0 if device `device` (or the current one when < 0) is compute capability 10.x, else SELD_ENODEVICE. */
 SELD_API int seld_device_check(int device);

@@ -21,6 +21,7 @@ _vp, _i, _i64, _u64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64, _c.c_f
 SIGNATURES = {
     'seld_last_error': (_c.c_char_p, []),
     'seld_version': (_i, []),
+    'seld_launch_count': (_i64, []),
     'seld_device_check': (_i, [_i]),
     'seld_plan_create': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _c.POINTER(_vp)]),
     'seld_plan_destroy': (_i, [_vp]),

@@ -29,6 +29,9 @@ int cuda_fail(cudaError_t e, const char* what) {
     return SELD_ECUDA;
 }
 
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 int device_sm_count() {
     static std::atomic<int> cache[64];
     int dev = 0;
@@ -617,6 +620,7 @@ static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream)
     }
     extract_kernel<R, MODE, LAYOUT, EDGE, TC><<<(int)grid, teams * 64, tb + teams * wb, stream>>>(a);
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 
@@ -649,7 +653,8 @@ using namespace seld;
 extern "C" {
 
 const char* seld_last_error(void) { return g_last_error.c_str(); }
-int seld_version(void) { return 1; }
+int seld_version(void) { return 2; }
+int64_t seld_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int seld_device_check(int device) {
     int dev = device;
@@ -910,6 +915,7 @@ int seld_clip_max_decode(const uint32_t* clip_max_key_dev, int n_clips, float* c
     clip_max_decode_kernel<<<(n_clips + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(clip_max_key_dev,
                                                                                                   n_clips, clip_max_dev);
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 

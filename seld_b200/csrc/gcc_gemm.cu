@@ -223,6 +223,7 @@ int launch_gcc_gemm(const GccGemmArgs& g, int num_sms, cudaStream_t st) {
     if (grid > g.n_tiles) grid = g.n_tiles;
     gcc_gemm_kernel<<<(int)grid, 192, smem, st>>>(g);
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 

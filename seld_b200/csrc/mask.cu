@@ -137,6 +137,7 @@ static int launch_mask(const MaskArgs& a, int num_sms, cudaStream_t st) {
     dim3 grid((unsigned)(a.n_samples * a.n_chunks), (unsigned)a.splits);
     mask_kernel<T><<<grid, 256, smem, st>>>(a);
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 
@@ -232,6 +233,7 @@ extern "C" int seld_channel_remap(const float* in_dev, float* out_dev, int64_t n
     channel_remap_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_dev, out_dev, (unsigned)per_sample, (unsigned)n_chan,
                                                                             (unsigned)inner, table_dev);
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 
@@ -269,5 +271,6 @@ extern "C" int seld_channel_offset(const float* in_dev, float* out_dev, int64_t 
     channel_offset_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_dev, out_dev, (unsigned)per_sample, (unsigned)n_chan,
                                                                              (unsigned)n_first, offset_dev);
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }

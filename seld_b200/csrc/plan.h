@@ -39,6 +39,8 @@ struct seld_plan {
 namespace seld {
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
+// one more kernel of this library was launched (seld_launch_count: what bench.py reports as gpu_launches)
+void note_launch();
 // multiprocessor count of the CURRENT device, queried once per device (a process may drive several GPUs)
 int device_sm_count();
 // true the first time it is called for (slot, current device): "set this kernel attribute once per device"

@@ -257,6 +257,7 @@ int seld_finalize(int n_mels, int n_ch, const float* feat_in_dev, const uint32_t
                                                             mean_dev, std_dev, eps, feat_out_dev);
     }
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 
@@ -287,9 +288,11 @@ int seld_stats(int n_mels, int n_ch, const float* feat_dev, const uint32_t* clip
                                                             n_ch, top_db, workspace_dev);
     }
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     const int n2 = 2 * row_len;
     stats_fold_kernel<<<(n2 + 127) / 128, 128, 0, st>>>(workspace_dev, blocks, n2, double(n_rows), acc_dev);
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 
@@ -298,6 +301,7 @@ int seld_stats_finish(int n_mels, int n_ch, const double* acc_dev, float* mean_d
     const int n = n_mels * n_ch;
     stats_finish_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(acc_dev, n, mean_dev, std_dev);
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 

@@ -122,6 +122,7 @@ static int launch_spec(const seld_plan* plan, const float* wav, int n_chan, long
                                                                   reinterpret_cast<const float2*>(plan->tw_t),
                                                                   reinterpret_cast<float2*>(spec));
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 
@@ -156,6 +157,7 @@ int seld_foa_iv(const float* spec_dev, int64_t n, float eps, float* iv_dev, void
     foa_iv_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float2*>(spec_dev), n, eps,
                                                                               iv_dev);
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 
@@ -172,6 +174,7 @@ int seld_gcc(const float* spec_dev, int n_chan, int64_t n_frames, int n_bins, in
                                                                                      n_chan, n_frames, n_bins, n_lags,
                                                                                      first_lag, gcc_dev);
     SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
     return SELD_OK;
 }
 

@@ -165,7 +165,7 @@ def new_accumulator(n_mels, n_ch, device):
     return torch.zeros(2 * n_mels * n_ch + 1, dtype=torch.float64, device=device)
 
 
-def partial_statistics(feat, clip_max_key=None, t_valid=None, acc=None, top_db=TOP_DB):
+def partial_statistics(feat, clip_max_key=None, t_valid=None, acc=None, top_db=TOP_DB, workspace=None):
     """Add this shard's per-(mel, chan) {sum, sum of squares, row count} to `acc` (float64 [2*n_mels*C + 1])."""
     feat4, (n_clips, t_out, n_mels, n_ch) = _feat_dims(feat)
     if t_valid is None:
@@ -174,7 +174,9 @@ def partial_statistics(feat, clip_max_key=None, t_valid=None, acc=None, top_db=T
         acc = new_accumulator(n_mels, n_ch, feat.device)
     lib = _lib.load()
     with torch.cuda.device(feat.device):
-        ws = torch.empty(lib.seld_stats_workspace_doubles(n_mels, n_ch), dtype=torch.float64, device=feat.device)
+        ws = workspace
+        if ws is None:
+            ws = torch.empty(lib.seld_stats_workspace_doubles(n_mels, n_ch), dtype=torch.float64, device=feat.device)
         _lib.check(lib.seld_stats(n_mels, n_ch, _lib.ptr(feat4), _lib.ptr(clip_max_key), n_clips, t_out,
                                   int(min(t_valid, t_out)), float(top_db), _lib.ptr(ws), _lib.ptr(acc),
                                   _lib.current_stream_ptr()))
@@ -190,10 +192,18 @@ def allreduce_statistics(acc):
     return acc
 
 
-def finish_statistics(acc, n_mels, n_ch):
+def stats_workspace(n_mels, n_ch, device):
+    """Scratch of partial_statistics (per-block partial sums), for callers that keep static buffers (CUDA graphs)."""
+    n = int(_lib.load().seld_stats_workspace_doubles(n_mels, n_ch))
+    return torch.empty(n, dtype=torch.float64, device=device)
+
+
+def finish_statistics(acc, n_mels, n_ch, mean=None, std=None):
     """(mean, std) float32 [1, n_mels, C] from the accumulators: population std, as numpy's in the reference."""
-    mean = torch.empty(1, n_mels, n_ch, dtype=torch.float32, device=acc.device)
-    std = torch.empty_like(mean)
+    if mean is None:
+        mean = torch.empty(1, n_mels, n_ch, dtype=torch.float32, device=acc.device)
+    if std is None:
+        std = torch.empty_like(mean)
     with torch.cuda.device(acc.device):
         _lib.check(_lib.load().seld_stats_finish(n_mels, n_ch, _lib.ptr(acc), _lib.ptr(mean), _lib.ptr(std),
                                                  _lib.current_stream_ptr()))
@@ -214,13 +224,75 @@ def extract_normalized_dataset(wav, sample_rate, mode='foa', n_mels=64, t_out=No
     return feat, mean, std
 
 
+class DatasetStep:
+    """The reference's whole `__main__` (feature_extractor.py:294-307) for this rank's resident shard on STATIC buffers:
+    fused extract -> per-bin statistics -> all-reduce (N > 1) -> top_db clamp + normalise.  `run()` enqueues the launches;
+    `capture()` records them -- the NCCL all-reduce included -- into one CUDA graph and `replay()` submits that graph: at
+    75 clips per GPU (BASELINE.json config 4 at N = 8) the step is ~1.5 ms and eight launches plus a collective are a
+    visible share of it."""
+
+    def __init__(self, wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', **kwargs):
+        self.wav, self.sample_rate, self.mode, self.n_mels, self.layout, self.kwargs = wav, sample_rate, mode, n_mels, layout, dict(kwargs)
+        dev = wav.device
+        n_clips = wav.shape[0]
+        n_samples = wav.shape[2] if layout == 'planar' and wav.dtype != torch.int16 else wav.shape[1]
+        with torch.cuda.device(dev):
+            plan = get_plan(sample_rate, mode=mode, n_mels=n_mels, **{k: v for k, v in kwargs.items() if k != 'pad'})
+        self.t_raw = plan.num_frames(n_samples + 2 * int(kwargs.get('pad', 0)))
+        self.t_out = self.t_raw if t_out is None else int(t_out)
+        self.n_ch = plan.n_out_ch
+        self.feat = torch.empty(n_clips, self.t_out, n_mels, self.n_ch, dtype=torch.float32, device=dev)
+        self.key = torch.empty(n_clips, dtype=torch.int32, device=dev)
+        self.acc = new_accumulator(n_mels, self.n_ch, dev)
+        self.ws = stats_workspace(n_mels, self.n_ch, dev)
+        self.mean = torch.empty(1, n_mels, self.n_ch, dtype=torch.float32, device=dev)
+        self.std = torch.empty_like(self.mean)
+        self.graph = None
+
+    def run(self, events=None):
+        """Enqueue one step on the current stream.  events: optional 4 CUDA events recorded around the three stages."""
+        if events: events[0].record()
+        extract_batch(self.wav, self.sample_rate, self.mode, self.n_mels, self.t_out, self.layout, self.feat, self.key, **self.kwargs)
+        if events: events[1].record()
+        self.acc.zero_()
+        partial_statistics(self.feat, self.key, self.t_raw, self.acc, workspace=self.ws)
+        allreduce_statistics(self.acc)
+        finish_statistics(self.acc, self.n_mels, self.n_ch, self.mean, self.std)
+        if events: events[2].record()
+        finalize_(self.feat, self.key, self.t_raw, self.mean, self.std)
+        if events: events[3].record()
+        return self.feat, self.mean, self.std
+
+    def capture(self, warmup=2):
+        """Record the step into a CUDA graph (after `warmup` eager runs on a side stream, as graph capture requires)."""
+        dev = self.wav.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self.run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.run()
+        self.graph = graph
+        return self
+
+    def replay(self):
+        self.graph.replay()
+        return self.feat, self.mean, self.std
+
+
 class HostDatasetExtractor:
     """End-to-end form with HOST buffers: pinned wav in, pinned normalised features out.
 
     The reference's `__main__` touches every clip three times on the host (extract, concatenate for mean/std,
-    normalise).  Here clips stream host -> device in chunks on a copy stream, double-buffered against the extract
-    kernel; features stay resident in HBM until the (all-reduced) statistics are known, then are normalised in
-    place and streamed back.  PCIe is the bound of this path, not the kernels.
+    normalise).  Here clips stream host -> device in chunks on an H2D stream, double-buffered against the extract
+    kernel; features stay resident in HBM until the (all-reduced) statistics are known, then are normalised chunk by
+    chunk and streamed back on a separate D2H stream.  PCIe is the bound of this path, not the kernels -- and PCIe is
+    full duplex: `submit()` only enqueues, so the upload of the NEXT dataset (or the next pass) runs while the previous
+    one's features are still on their way down (two feature buffers, both DMA engines busy).  `run()` = submit + wait.
     """
 
     def __init__(self, n_clips, n_samples, sample_rate, mode='foa', n_mels=64, t_out=None, chunk_clips=24,
@@ -235,53 +307,66 @@ class HostDatasetExtractor:
             self.t_out = self.t_raw if t_out is None else int(t_out)
             self.layout = 'interleaved' if dtype == torch.int16 else layout
             self.dtype = dtype
+            n_ch = self.plan.n_out_ch
             shape = (self.chunk, 4, n_samples) if self.layout == 'planar' else (self.chunk, n_samples, 4)
             self.stage = [torch.empty(shape, dtype=dtype, device=self.device) for _ in range(2)]
-            self.feat = torch.empty(self.n_clips, self.t_out, n_mels, self.plan.n_out_ch, dtype=torch.float32,
-                                    device=self.device)
-            self.key = torch.empty(self.n_clips, dtype=torch.int32, device=self.device)
-            self.copy_stream = torch.cuda.Stream(device=self.device)
+            self.feat = [torch.empty(self.n_clips, self.t_out, n_mels, n_ch, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self.key = [torch.empty(self.n_clips, dtype=torch.int32, device=self.device) for _ in range(2)]
+            self.acc = [new_accumulator(n_mels, n_ch, self.device) for _ in range(2)]
+            self.ws = stats_workspace(n_mels, n_ch, self.device)
+            self.h2d_stream = torch.cuda.Stream(device=self.device)
+            self.d2h_stream = torch.cuda.Stream(device=self.device)
             self.h2d_done = [torch.cuda.Event() for _ in range(2)]
             self.stage_free = [torch.cuda.Event() for _ in range(2)]
+            self.feat_free = [torch.cuda.Event() for _ in range(2)]      # the D2H of the previous dataset in this buffer is done
+            for e in self.stage_free + self.feat_free:
+                e.record(torch.cuda.current_stream(self.device))
+        self.n_submitted = 0
         self.h2d_bytes = self.n_clips * 4 * self.n_samples * (2 if dtype == torch.int16 else 4)
-        self.d2h_bytes = self.feat.numel() * 4
+        self.d2h_bytes = self.feat[0].numel() * 4
 
-    def run(self, wav_host, out_host):
+    def submit(self, wav_host, out_host):
         """wav_host: pinned [n_clips, 4, L] float32 (planar), [n_clips, L, 4] float32 (interleaved) or int16 (PCM);
-        out_host: pinned float32 [n_clips, t_out, n_mels, C].
-        Returns (mean, std) on the device.  Synchronises before returning (the result is on the host)."""
-        lib = _lib.load()
+        out_host: pinned float32 [n_clips, t_out, n_mels, C].  Enqueues everything and returns (mean, std, done event):
+        the result is on the host once `done` has completed.  Up to two datasets may be in flight."""
         main = torch.cuda.current_stream(self.device)
         n_ch = self.plan.n_out_ch
+        fb = self.n_submitted & 1
+        self.n_submitted += 1
+        feat, key, acc = self.feat[fb], self.key[fb], self.acc[fb]
         with torch.cuda.device(self.device):
-            acc = new_accumulator(self.n_mels, n_ch, self.device)
-            for e in self.stage_free:
-                e.record(main)
+            main.wait_event(self.feat_free[fb])
+            acc.zero_()
             starts = list(range(0, self.n_clips, self.chunk))
             for i, s in enumerate(starts):
                 n = min(self.chunk, self.n_clips - s)
                 b = i & 1
-                with torch.cuda.stream(self.copy_stream):
-                    self.copy_stream.wait_event(self.stage_free[b])
+                with torch.cuda.stream(self.h2d_stream):
+                    self.h2d_stream.wait_event(self.stage_free[b])
                     self.stage[b][:n].copy_(wav_host[s:s + n], non_blocking=True)
-                    self.h2d_done[b].record(self.copy_stream)
+                    self.h2d_done[b].record(self.h2d_stream)
                 main.wait_event(self.h2d_done[b])
                 extract_batch(self.stage[b][:n], self.sample_rate, mode=self.mode, n_mels=self.n_mels, t_out=self.t_out,
-                              layout=self.layout, out=self.feat[s:s + n], key=self.key[s:s + n], **self.kwargs)
+                              layout=self.layout, out=feat[s:s + n], key=key[s:s + n], **self.kwargs)
                 self.stage_free[b].record(main)
-            partial_statistics(self.feat, self.key, self.t_raw, acc)
+            partial_statistics(feat, key, self.t_raw, acc, workspace=self.ws)
             allreduce_statistics(acc)
             mean, std = finish_statistics(acc, self.n_mels, n_ch)
             # normalise chunk by chunk so the device -> host copies overlap the remaining normalisation
-            done = torch.cuda.Event()
             for s in starts:
                 n = min(self.chunk, self.n_clips - s)
-                finalize_(self.feat[s:s + n], self.key[s:s + n], self.t_raw, mean, std)
-                done.record(main)
-                with torch.cuda.stream(self.copy_stream):
-                    self.copy_stream.wait_event(done)
-                    out_host[s:s + n].copy_(self.feat[s:s + n], non_blocking=True)
+                finalize_(feat[s:s + n], key[s:s + n], self.t_raw, mean, std)
                 done = torch.cuda.Event()
-            self.copy_stream.synchronize()
-            main.synchronize()
+                done.record(main)
+                with torch.cuda.stream(self.d2h_stream):
+                    self.d2h_stream.wait_event(done)
+                    out_host[s:s + n].copy_(feat[s:s + n], non_blocking=True)
+            self.feat_free[fb] = torch.cuda.Event()
+            self.feat_free[fb].record(self.d2h_stream)
+        return mean, std, self.feat_free[fb]
+
+    def run(self, wav_host, out_host):
+        """One dataset, synchronously: returns (mean, std) on the device once the features are on the host."""
+        mean, std, done = self.submit(wav_host, out_host)
+        done.synchronize()
         return mean, std

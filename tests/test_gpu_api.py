@@ -82,3 +82,54 @@ def test_extract_seldnet_data_end_to_end(tmp_path, mode):
     assert np.abs(mean - allf.mean(0, keepdims=True)).max() <= 1e-4
     n0 = np.load(no / f'{sorted(wavs)[0]}.npy')
     assert n0.shape == (3000, 64, c) and abs(float(n0.mean())) < 1.0
+
+
+@pytest.mark.parametrize('mode', ['foa', 'mic'])
+def test_dataset_step_eager_and_cuda_graph_match_the_plain_calls(mode):
+    """pipeline.DatasetStep (static buffers; the whole extract -> statistics -> normalise step as ONE CUDA graph) gives the
+    same bits as the individual calls, replay after replay."""
+    from seld_b200 import pipeline
+    from seld_b200.synth import make_clips
+    wav = make_clips(range(40, 46), 480 * 120).cuda()
+    want, mean, std = pipeline.extract_normalized_dataset(wav, 24000, mode=mode, t_out=100, **PROD)
+    step = pipeline.DatasetStep(wav, 24000, mode=mode, t_out=100, **PROD)
+    feat, m, s = step.run()
+    assert torch.equal(feat, want) and torch.equal(m, mean) and torch.equal(s, std)
+    step.capture()
+    for _ in range(3):
+        feat.zero_()
+        feat, m, s = step.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(feat, want) and torch.equal(m, mean) and torch.equal(s, std)
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'int16'])
+def test_host_dataset_extractor_pipelined_submits(dtype):
+    """End-to-end form with pinned host buffers: one synchronous run == the device-resident step, and two datasets in
+    flight (upload of the second overlapping the download of the first) both arrive intact."""
+    from seld_b200 import pipeline
+    from seld_b200.synth import make_clips
+    n, L = 7, 480 * 90
+    wav = make_clips(range(60, 60 + n), L)
+    if dtype == 'int16':
+        pcm = torch.clamp(torch.round(wav * 32768.0), -32768, 32767).to(torch.int16)
+        host_in = pcm.transpose(1, 2).contiguous().pin_memory()
+        dev_in = (pcm.to(torch.float32) / 32768.0).cuda()
+        ex = pipeline.HostDatasetExtractor(n, L, 24000, mode='foa', t_out=80, chunk_clips=3, dtype=torch.int16, **PROD)
+    else:
+        host_in = wav.pin_memory()
+        dev_in = wav.cuda()
+        ex = pipeline.HostDatasetExtractor(n, L, 24000, mode='foa', t_out=80, chunk_clips=3, **PROD)
+    want, mean, std = pipeline.extract_normalized_dataset(dev_in, 24000, mode='foa', t_out=80, **PROD)
+    outs = [torch.empty(n, 80, 64, 7).pin_memory() for _ in range(3)]
+    m, s = ex.run(host_in, outs[0])
+    assert torch.equal(outs[0], want.cpu()) and torch.equal(m, mean) and torch.equal(s, std)
+    host_b = (host_in // 2) if dtype == 'int16' else (host_in * 0.5)
+    host_b = host_b.contiguous().pin_memory()
+    pend = [ex.submit(host_in, outs[1]), ex.submit(host_b, outs[2])]
+    for _, _, done in pend:
+        done.synchronize()
+    assert torch.equal(outs[1], want.cpu())
+    dev_b = (host_b.to(torch.float32) / 32768.0).transpose(1, 2).contiguous().cuda() if dtype == 'int16' else host_b.cuda()
+    want_b, _, _ = pipeline.extract_normalized_dataset(dev_b, 24000, mode='foa', t_out=80, **PROD)
+    assert torch.equal(outs[2], want_b.cpu())
