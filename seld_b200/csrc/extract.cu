@@ -93,6 +93,14 @@ static int frames_per_team(int dflt) {   // consecutive frames a team handles pe
 }
 
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
+#ifndef SELD_EARLY_TAIL
+#define SELD_EARLY_TAIL 0
+#endif
+// FOA experiment (kept off): request the next frame's 15 new taps right after the bin phase, so that their latency hides
+// behind the gather and the row store instead of being waited for at the top of the frame (16 % of the stall samples).
+// Measured, 600 clips: 10.37 ms with it, 9.25 ms without -- 30 more live registers at the 128-register budget of four
+// warps per scheduler cost more (112 B of spills, a tighter gather) than the exposed load.
+constexpr bool kEarlyTail = SELD_EARLY_TAIL;
 #ifndef SELD_GCC_DEAD
 #define SELD_GCC_DEAD 1
 #endif
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
 
     // everything after the team's two packed FFTs: mel pieces, gather, GCC, row store, running clip maximum.
     // mine: this team has a frame; part (fused GCC only): the partner team has one whose accumulator this team helps read.
-    auto finish_frame = [&](bool mine, bool part, int clip, int t, float* row) {
+    auto finish_frame = [&](bool mine, bool part, int clip, int t, float* row, auto&& early) {
         float mx = -INFINITY;
         if constexpr (FUSED) {
             if (mine) {
@@ -358,6 +366,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
             team_bar(bar_id);                                            // both spectra are in place
             bin_phase<R, MODE, TM>(S0, S1, tb, X, 1e-8f, u, taddr + TMEM_COL_W01);
             team_bar(bar_id);
+            early();                                                     // (FOA: the next frame's new samples are requested here)
             mx = a.seg_major ? gather_lanes<MODE>(X, tb, acc, a.n_mels, u) : gather_phase<MODE>(X, tb, acc, a.n_mels, u);
             if constexpr (MODE == MODE_MIC) {
                 team_bar(bar_id);                                        // pieces consumed: X is the GCC exchange buffer now
@@ -440,7 +449,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                     __syncwarp();
                     stage2();
                 }
-                if (mine || part) finish_frame(mine, part, clip, t, row);
+                if (mine || part) finish_frame(mine, part, clip, t, row, [] {});
             }
         }
     } else {
@@ -490,6 +499,25 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         const bool keep_ok = KEEP && a.hop == SH * 32;
         const unsigned tkeep = taddr + TMEM_COL_KEEP + 64 * (warp >> 2);
         int prev_clip = -1, prev_t = -2;
+        // taps [n_lo, n_hi) of the frame starting at sample `fs` of clip `c` (this warp's channel pair) -> r[]
+        auto load_taps = [&](int c, long long fs, int n_lo, int n_hi, float2* r) {
+            if constexpr (LAYOUT == LAYOUT_PCM16_LC) {
+                const float* p = reinterpret_cast<const float*>(reinterpret_cast<const short*>(a.wav) + ((long long)c * a.n_samples + fs + lane) * 4 + 2 * h);
+#pragma unroll
+                for (int n2 = 0; n2 < R; ++n2) if (n2 >= n_lo && n2 < n_hi) r[n2].x = p[64 * n2];
+            } else if constexpr (LAYOUT == LAYOUT_INTERLEAVED_LC) {
+                const float2* p = reinterpret_cast<const float2*>(a.wav + ((long long)c * a.n_samples + fs + lane) * 4 + 2 * h);
+#pragma unroll
+                for (int n2 = 0; n2 < R; ++n2) if (n2 >= n_lo && n2 < n_hi) r[n2] = p[64 * n2];
+            } else {
+                const float* pa = a.wav + ((long long)c * 4 + 2 * h) * a.n_samples + fs + lane;
+                const float* pb = pa + a.n_samples;
+#pragma unroll
+                for (int n2 = 0; n2 < R; ++n2) if (n2 >= n_lo && n2 < n_hi) r[n2] = make_float2(pa[32 * n2], pb[32 * n2]);
+            }
+        };
+        // (kEarlyTail: the SH new taps of the team's NEXT frame requested right after the bin phase)
+        bool have_tail = false;                       // every frame but a warp's first gets its tail early
         // (prefetching just the 15 new taps of the next frame in 30 registers was tried on top of this: 104 B of spills and
         //  9.58 ms instead of 9.06)
         // (Fused GCC: deferring a frame's epilogue into the next iteration -- accumulators and staged rows double-buffered, the
@@ -503,7 +531,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
             const long long gpart_next = FUSED ? frame_index(sc, fi, pteam) : -1;
             if constexpr (FUSED) {
                 if (!mine) {                              // only the partner has a frame: help read its accumulator
-                    finish_frame(false, true, 0, 0, nullptr);
+                    finish_frame(false, true, 0, 0, nullptr, [] {});
                     g = g_next;
                     gpart = gpart_next;
                     continue;
@@ -520,24 +548,11 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                         tmem_ld16(tkeep, rf);
                         tmem_ld16(tkeep + 16, rf + 16);
                         tmem_ld2(tkeep + 32, rf[32], rf[33]);                     // taps 0 .. 16
-                        if constexpr (LAYOUT == LAYOUT_PCM16_LC) {
-                            const float* p = reinterpret_cast<const float*>(reinterpret_cast<const short*>(a.wav) +
-                                                                            ((long long)clip * a.n_samples + start + lane) * 4 + 2 * h);
-#pragma unroll
-                            for (int n2 = R - SH; n2 < R; ++n2) raw[n2].x = p[64 * n2];
-                        } else if constexpr (LAYOUT == LAYOUT_INTERLEAVED_LC) {
-                            const float2* p = reinterpret_cast<const float2*>(a.wav + ((long long)clip * a.n_samples + start + lane) * 4 + 2 * h);
-#pragma unroll
-                            for (int n2 = R - SH; n2 < R; ++n2) raw[n2] = p[64 * n2];
-                        } else {
-                            const float* pa = a.wav + ((long long)clip * 4 + 2 * h) * a.n_samples + start + lane;
-                            const float* pb = pa + a.n_samples;
-#pragma unroll
-                            for (int n2 = R - SH; n2 < R; ++n2) raw[n2] = make_float2(pa[32 * n2], pb[32 * n2]);
-                        }
                     } else {
-                        request(g);
+                        load_taps(clip, start, 0, R - SH, raw);
                     }
+                    if (!(kEarlyTail && have_tail)) load_taps(clip, start, R - SH, R, raw);   // (else requested before the previous gather)
+                    have_tail = true;
                     if (keep_ok) {                                                // taps 15 .. 31 are taps 0 .. 16 of the next frame
                         const float* rf = reinterpret_cast<const float*>(raw);
                         tmem_st16(tkeep, rf + 2 * SH);
@@ -570,7 +585,15 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                 else stage1_fft_store<R>(v, tb, E, lane);
                 __syncwarp();
                 stage2();
-                finish_frame(true, gpart >= 0, clip_now, t_now, row);
+                finish_frame(true, gpart >= 0, clip_now, t_now, row, [&] {
+                    if constexpr (KEEP && kEarlyTail) {
+                        if (g_next >= 0) {
+                            const int c2 = int(g_next / a.frames_per_clip);
+                            const int t2 = a.t_lo + int(g_next - (long long)c2 * a.frames_per_clip);
+                            load_taps(c2, (long long)t2 * a.hop - G::N / 2 + a.origin, R - SH, R, raw);
+                        }
+                    }
+                });
             }
             g = g_next;
             gpart = gpart_next;
