@@ -32,6 +32,10 @@ extern "C" {
 
 #define SELD_MODE_FOA 0 /* 4 log-mel + 3 intensity-vector channels  (reference feature_extractor.py:74-77) */
 #define SELD_MODE_MIC 1 /* 4 log-mel + 6 GCC-PHAT channels           (reference feature_extractor.py:78-80) */
+#define SELD_MODE_FOA_TF 2 /* the TensorFlow variant of the FOA features (reference data_loader.py:310-349, get_preprocessed_x_tf):
+                              mel bank applied to |X| (not |X|^2), dB = 20 log10(mel) with no floor before the top_db clamp (tfio dbscale),
+                              frames start at sample t * hop with a zero-padded tail (tf.signal.stft(pad_end=True)); the caller passes
+                              tf.signal.hann_window and tf.signal.linear_to_mel_weight_matrix as window / mel table; n_fft = 1024 */
 
 #define SELD_LAYOUT_PLANAR_CL 0      /* wav[clip][chan][sample]  (torchaudio.load layout, feature_extractor.py:43) */
 #define SELD_LAYOUT_INTERLEAVED_LC 1 /* wav[clip][sample][chan]  (one 128-bit load = one time step of 4 channels) */
@@ -123,6 +127,14 @@ SELD_API int seld_extract_pcm16(seld_plan_t plan, const int16_t* pcm_dev, int n_
 SELD_API int seld_extract_chunks(seld_plan_t plan, const float* wav_dev, int layout, int n_chunks, int64_t n_samples, int t_out,
                                  float* feat_raw_dev, uint32_t* chunk_max_key_dev, void* workspace_dev, int64_t workspace_bytes,
                                  void* stream);
+
+/*
+ * Fused extractor for SELD_MODE_FOA_TF plans (reference data_loader.py:310-349, consumed by train.py:210-261 get_tdm_dataset):
+ * ceil(n_samples / hop) frames per clip, frame t = samples [t * hop, t * hop + n_fft) with zeros past the end; rows >= that
+ * count are zero; the log-mel block is un-clamped (pass the keys to seld_finalize, top_db = 80), -inf where the mel sum is 0.
+ */
+SELD_API int seld_extract_tf(seld_plan_t plan, const float* wav_dev, int layout, int n_clips, int64_t n_samples, int t_out,
+                             float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream);
 
 SELD_API int seld_clip_max_decode(const uint32_t* clip_max_key_dev, int n_clips, float* clip_max_dev, void* stream);
 

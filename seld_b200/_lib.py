@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('SELD_B200_LIB') or os.path.join(_HERE, 'libseld_b200.so')      # (override: kernel experiments only)
 
-MODE_FOA, MODE_MIC = 0, 1
+MODE_FOA, MODE_MIC, MODE_FOA_TF = 0, 1, 2
 LAYOUT_PLANAR_CL, LAYOUT_INTERLEAVED_LC = 0, 1
 RNG_PHILOX_COUNTER, RNG_TF_EAGER_COMPAT = 0, 1
 DTYPE_CODES = {'float32': 0, 'float64': 1, 'float16': 2, 'bfloat16': 3, 'int32': 4, 'int64': 5, 'int16': 6, 'uint8': 7}
@@ -29,6 +29,7 @@ SIGNATURES = {
     'seld_plan_num_frames': (_i64, [_vp, _i64]),
     'seld_extract': (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _i64, _vp]),
     'seld_extract_chunks': (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _i64, _vp]),
+    'seld_extract_tf': (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
     'seld_extract_workspace_bytes': (_i64, [_vp, _i, _i64, _i]),
     'seld_extract_pcm16': (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i64, _vp]),
     'seld_clip_max_decode': (_i, [_vp, _i, _vp, _vp]),

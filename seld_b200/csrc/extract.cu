@@ -77,6 +77,7 @@ struct ExtractArgs {
     int x_zero_f2;            // float2 elements of the piece buffer that must read as zero where no piece is stored
     int gcc_tc;               // MIC, n_fft 1024, 64 lags: fused tensor-core lag projection (extract_core.cuh)
     const void* gcc_basis;    // fp16 [64 lags][1024] basis of that projection (x512), row-major
+    int tf_variant;           // FOA plan created with SELD_MODE_FOA_TF (magnitude mel, 20 log10, zero-padded tail)
     int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
     int origin;               // frame t starts at sample t*hop - n_fft/2 + origin (0: centred STFT; n_fft/2: uncentred chunks)
     int fpw;                  // consecutive frames per team per super-chunk
@@ -170,6 +171,9 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     using SP = SmemPlan<R, MODE, TC>;
     constexpr bool TM = SP::TM;
     constexpr bool FUSED = SP::tc;
+    // TC on a FOA plan selects the TensorFlow variant of the features (reference data_loader.py:310-349,
+    // get_preprocessed_x_tf): mel bank on |X|, 20 log10 without a floor, frames from sample 0 with a zero-padded tail
+    constexpr bool TFV = TC && MODE == MODE_FOA;
     // ---- CTA-shared tables
     unsigned char* p = smem;
     float2* s_tw_t = nullptr;
@@ -364,10 +368,10 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
             if (!mine) return;
         } else {
             team_bar(bar_id);                                            // both spectra are in place
-            bin_phase<R, MODE, TM>(S0, S1, tb, X, 1e-8f, u, taddr + TMEM_COL_W01);
+            bin_phase<R, MODE, TM, TFV>(S0, S1, tb, X, 1e-8f, u, taddr + TMEM_COL_W01);
             team_bar(bar_id);
             early();                                                     // (FOA: the next frame's new samples are requested here)
-            mx = a.seg_major ? gather_lanes<MODE>(X, tb, acc, a.n_mels, u) : gather_phase<MODE>(X, tb, acc, a.n_mels, u);
+            mx = a.seg_major ? gather_lanes<MODE, TFV>(X, tb, acc, a.n_mels, u) : gather_phase<MODE, TFV>(X, tb, acc, a.n_mels, u);
             if constexpr (MODE == MODE_MIC) {
                 team_bar(bar_id);                                        // pieces consumed: X is the GCC exchange buffer now
                 if (h == 0) {
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                             stage1_load_reflect_pcm16<R>(reinterpret_cast<const short*>(a.wav) + (long long)clip * 4 * a.n_samples,
                                                          a.n_samples, h, start, wreg, v, lane);
                         else
-                            stage1_load_reflect<R>(src, 2 * h, 2 * h + 1, start, wreg, v, lane);
+                            stage1_load_reflect<R>(src, 2 * h, 2 * h + 1, start, wreg, v, lane, TFV);
                         note_dead(v);
                         if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
                         else stage1_fft_store<R>(v, tb, E, lane);
@@ -652,6 +656,7 @@ static int launch_kernels(const seld_plan* plan, const ExtractArgs& a, cudaStrea
     int rc;
     if (a.layout == LAYOUT_PLANAR_CL) rc = launch_one<R, MODE, LAYOUT_PLANAR_CL, false, TC>(plan, a, stream);
     else if (a.layout == LAYOUT_INTERLEAVED_LC) rc = launch_one<R, MODE, LAYOUT_INTERLEAVED_LC, false, TC>(plan, a, stream);
+    else if constexpr (MODE == MODE_FOA && TC) { set_error("the TF-variant extractor takes float32 input"); return SELD_EUNSUPPORTED; }
     else rc = launch_one<R, MODE, LAYOUT_PCM16_LC, false, TC>(plan, a, stream);
     if (rc != SELD_OK) return rc;
     return launch_one<R, MODE, LAYOUT_PLANAR_CL, true, TC>(plan, a, stream);  // edge frames: layout taken from a.layout
@@ -661,6 +666,9 @@ template <int R, int MODE>
 static int launch_mode(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
     constexpr bool can_tc = (MODE == MODE_MIC && R == 32);
     if (can_tc && a.gcc_tc) return launch_kernels<R, MODE, can_tc>(plan, a, stream);
+    if constexpr (MODE == MODE_FOA && R == 32) {
+        if (a.tf_variant) return launch_kernels<R, MODE, true>(plan, a, stream);
+    }
     return launch_kernels<R, MODE, false>(plan, a, stream);
 }
 
@@ -707,6 +715,11 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
         return SELD_EUNSUPPORTED;
     }
     if (n_chan != 4) { set_error("the fused extractor needs exactly 4 channels"); return SELD_EUNSUPPORTED; }
+    const bool tf_variant = (mode == SELD_MODE_FOA_TF);
+    if (tf_variant) {
+        if (n_fft != 1024) { set_error("SELD_MODE_FOA_TF is built for n_fft = 1024 (reference data_loader.py:311-312)"); return SELD_EUNSUPPORTED; }
+        mode = SELD_MODE_FOA;
+    }
     if (mode != SELD_MODE_FOA && mode != SELD_MODE_MIC) { set_error("invalid mode"); return SELD_EINVAL; }
     if (win_length <= 0 || win_length > n_fft || hop_length <= 0 || n_mels <= 0 || sample_rate <= 0) {
         set_error("invalid STFT geometry");
@@ -728,6 +741,7 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
     plan->n_mels = n_mels;
     plan->n_chan = n_chan;
     plan->mode = mode;
+    plan->tf_variant = tf_variant ? 1 : 0;
     plan->n_bins = n_fft / 2 + 1;
     plan->n_out_ch = (mode == SELD_MODE_FOA) ? 7 : 10;
     cudaGetDevice(&plan->device);
@@ -844,7 +858,7 @@ int64_t seld_plan_num_frames(seld_plan_t plan, int64_t n_samples) {
 
 static int extract_common(seld_plan_t plan, const void* wav_void, int layout, int n_clips, int64_t n_samples, int t_out,
                           float* feat_raw_dev, uint32_t* clip_max_key_dev, void* workspace_dev, int64_t workspace_bytes,
-                          void* stream, bool centered = true) {
+                          void* stream, bool centered = true, bool pad_end = false) {
     const float* wav_dev = static_cast<const float*>(wav_void);
     if (!plan || !wav_dev || !feat_raw_dev || !clip_max_key_dev) { set_error("null argument"); return SELD_EINVAL; }
     if (layout != LAYOUT_PLANAR_CL && layout != LAYOUT_INTERLEAVED_LC && layout != LAYOUT_PCM16_LC) { set_error("invalid layout"); return SELD_EINVAL; }
@@ -854,7 +868,9 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
         set_error("reflect padding needs n_fft/2 < number of samples (torch.stft raises here too)");
         return SELD_EINVAL;
     }
-    if (!centered && n_samples < plan->n_fft) { set_error("an uncentred chunk needs at least n_fft samples"); return SELD_EINVAL; }
+    if (!centered && !pad_end && n_samples < plan->n_fft) { set_error("an uncentred chunk needs at least n_fft samples"); return SELD_EINVAL; }
+    if (pad_end != (plan->tf_variant != 0)) { set_error("seld_extract_tf and SELD_MODE_FOA_TF plans go together"); return SELD_EINVAL; }
+    if (pad_end && n_samples < 1) { set_error("empty clip"); return SELD_EINVAL; }
     if (n_clips == 0) return SELD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ExtractArgs a;
@@ -863,6 +879,8 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
     a.n_clips = n_clips;
     a.n_samples = n_samples;
     a.t_raw = centered ? int(1 + n_samples / plan->hop) : int(1 + (n_samples - plan->n_fft) / plan->hop);
+    if (pad_end) a.t_raw = int((n_samples + plan->hop - 1) / plan->hop);      // tf.signal.stft(pad_end=True): ceil(L / hop) frames
+    a.tf_variant = plan->tf_variant;
     a.origin = centered ? 0 : plan->n_fft / 2;
     a.t_out = t_out;
     a.t_tot = a.t_raw > t_out ? a.t_raw : t_out;
@@ -889,6 +907,7 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
         const long long half = plan->n_fft / 2;
         long long lo = centered ? (half + plan->hop - 1) / plan->hop : 0;
         long long hi = centered ? ((n_samples >= half) ? (n_samples - half) / plan->hop + 1 : 0) : a.t_raw;
+        if (pad_end) hi = (n_samples >= plan->n_fft) ? (n_samples - plan->n_fft) / plan->hop + 1 : 0;    // frames wholly inside the clip
         if (hi > a.t_raw) hi = a.t_raw;
         if (lo > hi) lo = hi;
         a.t_lo = int(lo);
@@ -930,6 +949,13 @@ int seld_extract_chunks(seld_plan_t plan, const float* wav_dev, int layout, int 
     if (layout != SELD_LAYOUT_PLANAR_CL && layout != SELD_LAYOUT_INTERLEAVED_LC) { set_error("invalid layout"); return SELD_EINVAL; }
     return extract_common(plan, wav_dev, layout, n_chunks, n_samples, t_out, feat_raw_dev, chunk_max_key_dev, workspace_dev,
                           workspace_bytes, stream, /*centered=*/false);
+}
+
+int seld_extract_tf(seld_plan_t plan, const float* wav_dev, int layout, int n_clips, int64_t n_samples, int t_out,
+                    float* feat_raw_dev, uint32_t* clip_max_key_dev, void* stream) {
+    if (layout != SELD_LAYOUT_PLANAR_CL && layout != SELD_LAYOUT_INTERLEAVED_LC) { set_error("invalid layout"); return SELD_EINVAL; }
+    return extract_common(plan, wav_dev, layout, n_clips, n_samples, t_out, feat_raw_dev, clip_max_key_dev, nullptr, 0, stream,
+                          /*centered=*/false, /*pad_end=*/true);
 }
 
 int seld_clip_max_decode(const uint32_t* clip_max_key_dev, int n_clips, float* clip_max_dev, void* stream) {

@@ -239,9 +239,10 @@ SELD_HD void stage1_load_interior(const ClipSrc& src, int ch_a, int ch_b, long l
 }
 
 // Edge frames: reflect without edge repeat (torch.stft center=True, pad_mode='reflect').
+// zero_tail: samples past the end read as zero instead (tf.signal.stft(pad_end=True), reference data_loader.py:320).
 template <int R>
 SELD_HD void stage1_load_reflect(const ClipSrc& src, int ch_a, int ch_b, long long frame_start, const float* wreg,
-                                 float2* v, int lane) {
+                                 float2* v, int lane, bool zero_tail = false) {
     const float* xa = src.base + ch_a * src.chan_stride;
     const float* xb = src.base + ch_b * src.chan_stride;
     const long long L = src.n_samples;
@@ -249,9 +250,10 @@ SELD_HD void stage1_load_reflect(const ClipSrc& src, int ch_a, int ch_b, long lo
     for (int n2 = 0; n2 < R; ++n2) {
         long long i = frame_start + lane + 32 * n2;
         if (i < 0) i = -i;
-        if (i >= L) i = 2 * (L - 1) - i;
+        const bool past = i >= L;
+        if (past) i = zero_tail ? 0 : 2 * (L - 1) - i;
         float a = 0.f, b = 0.f;
-        if (wreg[n2] != 0.f) {
+        if (wreg[n2] != 0.f && !(past && zero_tail)) {
             a = xa[i * src.samp_stride];
             b = xb[i * src.samp_stride];
         }
@@ -392,6 +394,16 @@ SELD_HD float rsqrt_ftz(float s) {      // one MUFU.RSQ; subnormal inputs flush 
 #endif
 }
 
+SELD_HD float sqrt_ftz(float s) {       // one MUFU.SQRT
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    return r;
+#else
+    return sqrtf(s);
+#endif
+}
+
 SELD_HD float2 unit_phasor(float2 a) {   // a / |a|, (0,0) for a == 0; scaled so |a|^2 neither under- nor overflows
     float m = fmaxf(fabsf(a.x), fabsf(a.y));
     if (!(m > 0.f)) return make_float2(0.f, 0.f);
@@ -475,7 +487,7 @@ SELD_HD float pack_half2(float lo, float hi) {          // two floats -> one 32-
 #endif
 }
 
-template <int R, int MODE, bool W_TMEM = false>
+template <int R, int MODE, bool W_TMEM = false, bool MAG = false>
 SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, float eps, int u,      // u: team lane, 0..TL-1
                        unsigned taddr_w01 = 0) {                                                    // W_TMEM: mel weights from tensor memory
     using G = Geo<R>;
@@ -508,6 +520,12 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
         float val[NV];
 #pragma unroll
         for (int c = 0; c < 4; ++c) val[c] = fmaf(ch[c].x, ch[c].x, ch[c].y * ch[c].y);     // 4 |X_c|^2
+        if constexpr (MAG) {
+            // TF variant (reference data_loader.py:320-322): the mel bank is applied to |X|, not |X|^2; 4 |X| = sqrt(4 * 4 |X|^2)
+            // so that the 1/4 folded into the weights still applies
+#pragma unroll
+            for (int c = 0; c < 4; ++c) val[c] = sqrt_ftz(4.0f * val[c]);
+        }
         if constexpr (MODE == MODE_FOA) {
             // W = ch0, Y = ch1, Z = ch2, X = ch3; I = Re(conj(W) * {X, Y, Z})  (here 4 I)
             const float ix = fmaf(ch[0].x, ch[3].x, ch[0].y * ch[3].y);
@@ -561,13 +579,16 @@ SELD_HD float power_to_db(float pw) {
     const float v = fast_db(fmaxf(pw, 1e-10f));
     return (pw != pw) ? pw : v;
 }
+// TF variant: tfio dbscale = 10 log10(x^2) with NO floor (reference data_loader.py:323): log(0) = -inf survives until the
+// top_db clamp against the clip maximum
+SELD_HD float magnitude_to_db(float m) { return 2.0f * fast_db(m); }
 // running maximum that a NaN sticks to (torch's max propagates NaN)
 SELD_HD float max_nan(float m, float v) { return (v != v || m != m) ? NAN : fmaxf(m, v); }
 
 // ---------------------------------------------------------------- gather: pieces -> mel rows
 // Team lane u owns filters m = u, u + TL, ...: mel[m][c] = sum_{pieces of seg m} P.x + sum_{pieces of seg m-1} P.y, in
 // piece order.  Log-mel channels get 10 log10(max(., 1e-10)) here; returns the lane's maximum dB.
-template <int MODE>
+template <int MODE, bool MAG = false>
 SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_mels, int u) {
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int PSTRIDE = PieceGeo<MODE>::PSTRIDE;
@@ -590,7 +611,7 @@ SELD_HD float gather_phase(const float2* P, const Tables& tb, float* acc, int n_
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float v = power_to_db(sum[c]);
+            const float v = MAG ? magnitude_to_db(sum[c]) : power_to_db(sum[c]);
             mx = max_nan(mx, v);
             acc[m * C + c] = v;
         }
@@ -617,7 +638,7 @@ SELD_HD void seg_total(const float2* P, const Tables& tb, int seg, float2* A) {
     for (int c = 0; c < NV; ++c) A[c] = padd(padd(padd(rec[c], rec[kSegMajorPitch * PSTRIDE + c]), r2[c]), r3[c]);
 }
 
-template <int MODE>
+template <int MODE, bool MAG = false>
 SELD_HD float gather_lanes(const float2* P, const Tables& tb, float* acc, int n_mels, int u) {
     constexpr int NV = PieceGeo<MODE>::NV;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
@@ -651,7 +672,7 @@ SELD_HD float gather_lanes(const float2* P, const Tables& tb, float* acc, int n_
         for (int c = 0; c < NV; ++c) {
             float v = A[c].x + below[c];
             if (c < 4) {
-                v = power_to_db(v);
+                v = MAG ? magnitude_to_db(v) : power_to_db(v);
                 mx = max_nan(mx, v);
             }
             acc[u * C + c] = v;

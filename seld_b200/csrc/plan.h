@@ -10,6 +10,7 @@
 
 struct seld_plan {
     int sample_rate, n_fft, win_length, hop, n_mels, n_chan, mode;
+    int tf_variant;  // created with SELD_MODE_FOA_TF: magnitude mel, 20 log10 without a floor, zero-padded tail frames
     int n_bins;      // n_fft / 2 + 1
     int n_out_ch;    // 7 | 10
     int device;

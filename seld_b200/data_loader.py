@@ -15,8 +15,8 @@ drop-remainder rule follow the reference; random streams are this package's own 
 import numpy as np
 import torch
 
-__all__ = ['data_loader', 'seldnet_data_to_dataloader', 'get_preprocessed_x', 'frame_windows', 'overlap_and_add_mean',
-           'ensemble_outputs']
+__all__ = ['data_loader', 'seldnet_data_to_dataloader', 'get_preprocessed_x', 'get_preprocessed_x_tf', 'foa_intensity_vectors_tf',
+           'gcc_features_tf', 'TDM_aug', 'get_TDMset', 'normalize_over_clips', 'frame_windows', 'overlap_and_add_mean', 'ensemble_outputs']
 
 
 def _as_tensor(a, device):
@@ -177,6 +177,115 @@ def get_preprocessed_x(wav, sample_rate, mode='foa', n_mels=64, multiplier=5, ma
         plan = get_plan(sample_rate, mode=mode, n_mels=n_mels, **{k: v for k, v in kwargs.items() if k != 'pad'})
     pipeline.finalize_(feat, key, plan.num_frames(w.shape[-1] + 2 * int(kwargs.get('pad', 0))))
     return feat[0] if single else feat
+
+
+# --------------------------------------------------------------------------- TensorFlow-variant on-the-fly extractor
+def get_preprocessed_x_tf(wav, sr, mode='foa', n_mels=64, multiplier=5, max_label_length=600, win_length=1024,
+                          hop_length=480, n_fft=1024):
+    """reference data_loader.py:310-349 (behind train.py:210-261 get_tdm_dataset): one clip ``wav [4, L]`` (or a batch
+    ``[n, 4, L]``) -> CUDA float32 ``[max_label_length * multiplier, n_mels, 7]``: tf.signal.stft(pad_end=True) frames, mel
+    bank (tf.signal.linear_to_mel_weight_matrix) on |X|, tfio dbscale(top_db=80), intensity vectors through the same bank,
+    zero-padded / truncated.  One fused launch + the clamp.  mode='mic' raises like the reference does: its
+    gcc_features_tf slices the time axis and the concat with the log-mel block fails on the shape."""
+    from . import _lib, pipeline
+    if mode != 'foa':
+        raise ValueError('invalid mode')
+    _lib.require_device()
+    w = torch.as_tensor(wav)
+    single = w.dim() == 2
+    dev = w.device if w.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    w = (w.unsqueeze(0) if single else w).to(device=dev, dtype=torch.float32).contiguous()
+    max_len = int(max_label_length) * int(multiplier)
+    feat, key = pipeline.extract_batch_tf(w, sr, n_mels=n_mels, t_out=max_len, win_length=win_length, hop_length=hop_length, n_fft=n_fft)
+    pipeline.finalize_(feat, key, -(-w.shape[-1] // hop_length))
+    return feat[0] if single else feat
+
+
+def foa_intensity_vectors_tf(spectrogram, eps=1e-8):
+    """reference data_loader.py:237-251 for a complex ``[4, time, freq]`` tensor (stand-alone helper; the fused extractor
+    computes the same per bin)."""
+    s = torch.as_tensor(spectrogram)
+    c0 = torch.conj(s[0])
+    iv = torch.stack([(c0 * s[3]).real, (c0 * s[1]).real, (c0 * s[2]).real], 0)
+    norm = torch.clamp_min(torch.sqrt((iv ** 2).sum(0)), eps)
+    return iv / norm
+
+
+def gcc_features_tf(complex_specs, n_mels):
+    """reference data_loader.py:254-265, literally: irfft over the LAST axis of ``[chan, time, freq]``, then
+    ``concat(cc[-n_mels//2:], cc[:(n_mels+1)//2], axis=0)`` -- which slices FRAMES, not lags -> ``[pairs, n_mels, n_fft]``
+    (the reason the reference's mode='mic' TF path cannot be concatenated with the log-mel block)."""
+    s = torch.as_tensor(complex_specs)
+    out = []
+    for m in range(s.shape[0]):
+        for n in range(m + 1, s.shape[0]):
+            r = torch.conj(s[m]) * s[n]
+            cc = torch.fft.irfft(torch.exp(1j * torch.angle(r)), dim=-1)
+            out.append(torch.cat([cc[-(n_mels // 2):], cc[:(n_mels + 1) // 2]], 0))
+    return torch.stack(out, 0)
+
+
+def normalize_over_clips(x):
+    """train.py:232: ``(x - reduce_mean(x, 0)) / reduce_std(x, 0)`` -- statistics over the CLIP axis only, one per
+    (frame, mel, channel) -- for the stacked ``[n_clips, T, F, C]`` output of get_preprocessed_x_tf."""
+    x = torch.as_tensor(x)
+    return (x - x.mean(0)) / x.std(0, unbiased=False)
+
+
+STREAM_TDM = 0x110
+
+
+def TDM_aug(x, y, tdm_x, tdm_y, sr=24000, label_resolution=0.1, max_overlap_num=5, max_overlap_per_frame=2, min_overlap_sec=1,
+            max_overlap_sec=5, seed=0, return_draws=False):
+    """reference data_loader.py:188-234, time-domain mixing of single-class recordings into the clips before extraction.
+    x: list of ``[4, L]`` waveforms, y: list of ``[T_y, 4 * n_classes]`` labels, tdm_x / tdm_y: per class ``[4, frames]`` /
+    ``[time, 4 * n_classes]``.  Per clip, ``max_overlap_num`` classes are drawn with probability ~ 1 / (class length), and for
+    each a duration in [min, max) label frames, a position in the clip and a position in the class recording; label frames
+    that already hold ``max_overlap_per_frame`` events or the same class are skipped.  The tensors stay where they are (the
+    mixing runs on the device when they are CUDA tensors); lists are modified in place and returned, as in the reference.
+    Draws: this package's counter-based Philox stream (seed, clip index, STREAM_TDM, event) -- the reference's are
+    TensorFlow's unseeded stateful ops."""
+    from . import philox
+    n_cls = y[0].shape[-1] // 4
+    lo, hi = int(min_overlap_sec / label_resolution), int(max_overlap_sec / label_resolution)
+    spf = int(sr * label_resolution)
+    lens = np.array([int(k.shape[0]) for k in tdm_y], dtype=np.float64)
+    cdf = np.cumsum((1.0 / lens) / (1.0 / lens).sum())
+    draws = []
+    for i in range(len(x)):
+        frames_y = int(y[i].shape[0])
+        mine = []
+        for j in range(max_overlap_num):
+            w = philox.sample_words(int(seed), i, 1, STREAM_TDM, draw=j)[0].astype(np.uint64)
+            cls = int(np.searchsorted(cdf, (float(w[0]) + 0.5) / 4294967296.0))
+            cls = min(cls, len(tdm_y) - 1)
+            st = lo + int(w[1] % np.uint64(hi - lo))
+            off = int(w[2] % np.uint64(frames_y - st))
+            tdo = int(w[3] % np.uint64(int(tdm_y[cls].shape[0]) - st))
+            mine.append((cls, st, off, tdo))
+            frame_y = y[i][off:off + st]
+            nondup = 1 - frame_y[..., cls]
+            valid = (frame_y[..., :n_cls].sum(-1) < max_overlap_per_frame).to(frame_y.dtype) * nondup
+            if float(valid.sum()) == 0:
+                continue
+            y[i][off:off + st] += tdm_y[cls][tdo:tdo + st].to(y[i].device) * valid[:, None]
+            gain = valid.to(x[i].dtype).repeat_interleave(spf)[None, :].to(x[i].device)
+            x[i][:, off * spf:(off + st) * spf] += tdm_x[cls][:, tdo * spf:(tdo + st) * spf].to(x[i].device) * gain
+        draws.append(mine)
+    return (x, y, draws) if return_draws else (x, y)
+
+
+def get_TDMset(TDM_PATH):
+    """reference data_loader.py:170-185: the per-class recordings / labels written by the reference's TDM preparation
+    (``foa_dev_tdm/tdm_noise_<c>.joblib``, ``tdm_label_<c>.joblib``) -> lists of float32 tensors."""
+    import os
+    from glob import glob
+    import joblib
+    tdm_path = os.path.join(TDM_PATH, 'foa_dev_tdm')
+    class_num = len(glob(tdm_path + '/*label_*.joblib'))
+    tdm_x = [torch.as_tensor(np.asarray(joblib.load(os.path.join(tdm_path, f'tdm_noise_{c}.joblib')), dtype=np.float32)) for c in range(class_num)]
+    tdm_y = [torch.as_tensor(np.asarray(joblib.load(os.path.join(tdm_path, f'tdm_label_{c}.joblib')))) for c in range(class_num)]
+    return tdm_x, tdm_y
 
 
 # --------------------------------------------------------------------------- sliding-window evaluation (trainv2.py:158-192)

@@ -98,6 +98,41 @@ def extract_batch(wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='p
     return out, key
 
 
+def extract_batch_tf(wav, sample_rate, n_mels=64, t_out=None, layout='planar', out=None, key=None, win_length=1024,
+                     hop_length=480, n_fft=1024):
+    """The TensorFlow variant of the FOA features (reference data_loader.py:310-349 get_preprocessed_x_tf, the extractor
+    behind train.py:210-261 get_tdm_dataset) for a batch of clips: ceil(L / hop) frames from sample 0 with a zero-padded
+    tail, mel bank (tf.signal.linear_to_mel_weight_matrix) on |X|, 20 log10 without a floor, intensity vectors through the
+    same bank.  Returns (feat_raw [n_clips, t_out, n_mels, 7], keys): pass both to finalize_ for tfio's top_db=80 clamp."""
+    _check_cuda_f32(wav, 'wav')
+    if wav.dim() != 3:
+        raise ValueError('wav must be [n_clips, 4, L] or [n_clips, L, 4]')
+    if layout == 'planar':
+        n_clips, n_chan, n_samples = wav.shape
+        code = _lib.LAYOUT_PLANAR_CL
+    elif layout == 'interleaved':
+        n_clips, n_samples, n_chan = wav.shape
+        code = _lib.LAYOUT_INTERLEAVED_LC
+    else:
+        raise ValueError('layout must be "planar" or "interleaved"')
+    if n_chan != 4:
+        raise ValueError('the fused extractor needs exactly 4 channels')
+    with torch.cuda.device(wav.device):
+        plan = get_plan(sample_rate, mode='foa', n_mels=n_mels, n_fft=n_fft, win_length=win_length, hop_length=hop_length, variant='tf')
+        t_raw = plan.num_frames(n_samples)
+        t_out = t_raw if t_out is None else int(t_out)
+        shape = (n_clips, t_out, plan.n_mels, 7)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=wav.device)
+        elif tuple(out.shape) != shape:
+            raise ValueError(f'out must have shape {shape}')
+        if key is None:
+            key = torch.empty(n_clips, dtype=torch.int32, device=wav.device)
+        _lib.check(_lib.load().seld_extract_tf(plan.handle, _lib.ptr(wav), code, n_clips, n_samples, t_out, _lib.ptr(out),
+                                               _lib.ptr(key), _lib.current_stream_ptr()))
+    return out, key
+
+
 def clip_max_keys(max_db):
     """float32 per-clip maxima (dB) -> the order-preserving int32 keys finalize_ / partial_statistics expect (cached
     clip maxima of an earlier full-clip pass)."""

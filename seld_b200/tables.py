@@ -83,3 +83,27 @@ def gcc_operand_image(mat: np.ndarray) -> np.ndarray:
         out[:, r, :, u ^ (r % 8), :] = x[:, r, :, u, :]
     out = out.transpose(0, 2, 1, 3, 4)                          # [block][chunk][row][unit][e]
     return np.ascontiguousarray(out if rows != 64 else out[0])
+
+
+# --------------------------------------------------------------------------- TensorFlow variant (reference data_loader.py:310-349)
+def tf_hann_window(n: int) -> np.ndarray:
+    """tf.signal.hann_window(n, periodic=True) in float32 arithmetic: 0.5 - 0.5 cos(2 pi k / (n + even - 1))."""
+    even = 1 - n % 2
+    count = np.arange(n).astype(np.float32)
+    arg = np.float32(2 * np.pi) * count / np.float32(n + even - 1)
+    return (np.float32(0.5) - np.float32(0.5) * np.cos(arg)).astype(np.float32)
+
+
+def tf_mel_weight_matrix(n_mels: int, n_bins: int, sample_rate: int, lower_hz: float = 0.0, upper_hz=None) -> np.ndarray:
+    """tf.signal.linear_to_mel_weight_matrix(n_mels, n_bins, sample_rate, lower_hz, upper_hz) in float32 arithmetic:
+    HTK mel = 1127 ln(1 + f / 700); triangles linear in MEL between linspace(mel(lo), mel(hi), n_mels + 2); the DC row
+    is zero.  Every row has at most two adjacent non-zeros, which is what the extractor's piece form needs."""
+    f32 = np.float32
+    upper_hz = sample_rate // 2 if upper_hz is None else upper_hz
+    mel = lambda hz: (f32(1127.0) * np.log(f32(1.0) + hz / f32(700.0))).astype(f32)      # noqa: E731
+    lin = np.linspace(f32(0.0), f32(sample_rate) / f32(2.0), n_bins, dtype=f32)[1:]
+    bins_mel = mel(lin)[:, None]
+    edges = np.linspace(mel(np.asarray(f32(lower_hz))), mel(np.asarray(f32(upper_hz))), n_mels + 2, dtype=f32)
+    lower, center, upper = edges[None, :-2], edges[None, 1:-1], edges[None, 2:]
+    w = np.maximum(f32(0.0), np.minimum((bins_mel - lower) / (center - lower), (upper - bins_mel) / (upper - center)))
+    return np.concatenate([np.zeros((1, n_mels), dtype=f32), w.astype(f32)], 0)
