@@ -208,6 +208,22 @@ SELD_API int seld_channel_offset(const float* in_dev, float* out_dev, int64_t n_
                                  const float* offset_dev, void* stream);
 
 /*
+ * Fused training-batch augmentation (one read + one write of the batch; draws made on the device, no host random numbers):
+ *   level jitter   reference trainv2.py:120-124 random_ups_and_downs: N(0, level_stddev^2) per sample on channels [:4] (0 = off)
+ *   spatial        0 none | 1 foa_intensity_vec_aug (transforms.py:78-114, n_chan 7) | 2 acs_aug (:155-199, n_chan 17),
+ *                  applied consistently to the label coordinates y[n][t_y][4][n_classes] (y_in_dev / y_out_dev may be NULL)
+ *   masks          reference transforms.py:6-43 per `period`-frame chunk: time_n bands of < time_max frames, freq_n bands of
+ *                  < freq_max bins -- the same bands seld_mask draws for (seed, sample_offset) in PHILOX_COUNTER mode
+ * x_out[b,t,f,c] = keep(t,f) * sign_b[c] * (x_in[b,t,f,src_b[c]] + (src_b[c] < 4 ? offset_b : 0)).  Out of place when
+ * spatial != 0.  draws_out_dev (nullable) [n][2] int32: packed spatial draw (IV: flip bits 0..2, swap bit 3; ACS: swap
+ * index), level offset as float bits.  Streams: (seed, sample_offset + b, 0x100 | 0x101 | 0x102) as in transforms.py.
+ */
+SELD_API int seld_augment_batch(const float* x_in_dev, float* x_out_dev, int64_t n_samples, int64_t t, int64_t f, int n_chan,
+                                const float* y_in_dev, float* y_out_dev, int64_t t_y, int n_classes, int spatial, float level_stddev,
+                                int period, int time_max, int time_n, int freq_max, int freq_n, uint64_t seed, uint64_t sample_offset,
+                                int32_t* draws_out_dev, void* stream);
+
+/*
  * Stand-alone stages (API parity with the reference's public helpers; the hot path is seld_extract).
  *   seld_complex_spec     reference feature_extractor.py:153-173; spec_dev [n_chan][T][F] complex64 (frame-major;
  *                         the Python wrapper returns the [C, F, T] transposed view)

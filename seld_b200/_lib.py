@@ -40,6 +40,7 @@ SIGNATURES = {
     'seld_mask': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _i, _u64, _u64, _i, _vp, _vp, _vp]),
     'seld_channel_remap': (_i, [_vp, _vp, _i64, _i64, _i, _i64, _vp, _vp]),
     'seld_channel_offset': (_i, [_vp, _vp, _i64, _i64, _i, _i, _vp, _vp]),
+    'seld_augment_batch': (_i, [_vp, _vp, _i64, _i64, _i64, _i, _vp, _vp, _i64, _i, _i, _f, _i, _i, _i, _i, _i, _u64, _u64, _vp, _vp]),
     'seld_complex_spec': (_i, [_vp, _vp, _i, _i64, _f, _vp, _vp]),
     'seld_foa_iv': (_i, [_vp, _i64, _f, _vp, _vp]),
     'seld_gcc': (_i, [_vp, _i, _i64, _i, _i, _i, _vp, _vp]),

@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libseld_b200.so')
-SOURCES = ['extract.cu', 'post.cu', 'mask.cu', 'spec_ops.cu', 'gcc_gemm.cu']
-HEADERS = ['seld_common.cuh', 'extract_core.cuh', 'mel_pieces.h', 'plan.h', os.path.join('..', '..', 'include', 'seld_b200.h')]
+SOURCES = ['extract.cu', 'post.cu', 'mask.cu', 'augment.cu', 'spec_ops.cu', 'gcc_gemm.cu']
+HEADERS = ['seld_common.cuh', 'extract_core.cuh', 'mel_pieces.h', 'plan.h', 'philox.cuh', os.path.join('..', '..', 'include', 'seld_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
 

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 
-__all__ = ['mask', 'simple_mask', 'mask_batch_', 'sample_masks', 'random_ups_and_downs', 'set_seed', 'set_counter_seed', 'foa_intensity_vec_aug', 'acs_aug',
+__all__ = ['mask', 'simple_mask', 'mask_batch_', 'sample_masks', 'augment_batch', 'batch_augment', 'random_ups_and_downs', 'set_seed', 'set_counter_seed', 'foa_intensity_vec_aug', 'acs_aug',
            'mic_gcc_perm', 'channel_list', 'split_total_labels_to_sed_doa']
 
 _MAXINT32 = 2 ** 31 - 1
@@ -230,6 +230,66 @@ def sample_masks(time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, le
             out = x.clone(memory_format=torch.contiguous_format)
         mask_batch_(out, time_mask, freq_mask, period=period, seed=seed, sample_offset=first)
         return out, y
+    op.batched = True
+    return op
+
+
+# --------------------------------------------------------------------------- fused augmentation launch (device draws)
+_SPATIAL = {None: 0, 'none': 0, 'foa': 1, 'foa_iv': 1, 'acs': 2}
+
+
+def augment_batch(x, y=None, spatial=None, level_jitter=None, time_mask=None, freq_mask=None, period=100, seed=None,
+                  sample_offset=None, return_draws=False):
+    """ONE launch over a CUDA batch ``x [B, T, F, C]`` (+ one tiny launch over the labels ``y [B, T_y, 4 * n_classes]``) that
+    applies, with every draw made on the device: the level jitter of trainv2.py:120-124 (``level_jitter`` = stddev), the
+    spatial augmentation ``'foa'`` (foa_intensity_vec_aug, transforms.py:78-114) or ``'acs'`` (acs_aug, :155-199), and the
+    time / frequency masks of transforms.py:6-43 (``(max_size, n)`` per ``period``-frame chunk).  Returns new tensors
+    ``(x, y)`` -- bit-identical to foa_intensity_vec_aug / acs_aug, random_ups_and_downs and mask_batch_ applied one after
+    the other with the same ``seed`` and ``sample_offset`` (the Philox streams are shared)."""
+    _lib.require_device()
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4):
+        raise ValueError('x must be a CUDA tensor [B, T, F, C]')
+    xs = x.to(torch.float32).contiguous()
+    b, t, f, c = xs.shape
+    code = _SPATIAL.get(spatial)
+    if code is None:
+        raise ValueError('spatial must be None, "foa" or "acs"')
+    ys = yo = None
+    n_cls = t_y = 0
+    if y is not None and code != 0:
+        ys = torch.as_tensor(y).to(device=xs.device, dtype=torch.float32).contiguous()
+        if ys.dim() != 3 or ys.shape[0] != b or ys.shape[-1] % 4:
+            raise ValueError('y must be [B, T_y, 4 * n_classes]')
+        t_y, n_cls = ys.shape[1], ys.shape[2] // 4
+        yo = torch.empty_like(ys)
+    tm, tn = time_mask if time_mask else (0, 0)
+    fm, fn = freq_mask if freq_mask else (0, 0)
+    if (tn or fn) and t % period != 0:
+        raise ValueError("(spec time length / period)' rest must be 0")
+    seed, first = _draw_seed(b, seed, sample_offset)
+    out = torch.empty_like(xs)
+    draws = torch.empty(b, 2, dtype=torch.int32, device=xs.device) if return_draws else None
+    with torch.cuda.device(xs.device):
+        _lib.check(_lib.load().seld_augment_batch(_lib.ptr(xs), _lib.ptr(out), b, t, f, c, _lib.ptr(ys), _lib.ptr(yo), t_y, n_cls, code,
+                                                  float(level_jitter or 0.0), int(period), int(tm or 0), int(tn), int(fm or 0), int(fn),
+                                                  int(seed), int(first), _lib.ptr(draws), _lib.current_stream_ptr()))
+    y_out = yo if yo is not None else y
+    return (out, y_out, draws) if return_draws else (out, y_out)
+
+
+def batch_augment(spatial=None, level_jitter=None, time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None):
+    """The whole augmentation chain of train.py:157-165 / trainv2.py:134-138 as ONE batched transform for
+    ``data_loader.seldnet_data_to_dataloader(sample_transforms=[...])``: ``(x [B, T, F, C], y) -> (new x, new y)``."""
+    state = {'next_sample': 0}
+    lock = threading.Lock()
+
+    def op(x, y):
+        first = None
+        if seed is not None:
+            with lock:
+                first = state['next_sample']
+                state['next_sample'] += int(x.shape[0])
+        return augment_batch(x, y, spatial, level_jitter, time_mask, freq_mask, period, seed, first)
     op.batched = True
     return op
 

@@ -111,3 +111,49 @@ def test_seeded_sample_masks_draw_fresh_bands_every_batch():
     want = x.clone()
     T.mask_batch_(want, (24, 1), (16, 1), seed=1, sample_offset=8)
     assert torch.equal((want == 0), (b == 0))
+
+
+@pytest.mark.parametrize('spatial,c', [('foa', 7), ('acs', 17), (None, 7), (None, 10)])
+def test_fused_augment_batch_equals_the_separate_calls(spatial, c):
+    """seld_augment_batch draws on the device from the same Philox streams as the host-side functions: one launch ==
+    level jitter -> spatial augmentation -> time / frequency masks, bit for bit (and so == the oracle restatements)."""
+    g = torch.Generator().manual_seed(7)
+    x = (torch.rand(12, 300, 64, c, generator=g) - 0.5).cuda()
+    y = (torch.rand(12, 60, 56, generator=g) - 0.5).cuda()
+    seed, off = 1234, 500
+    got_x, got_y, draws = T.augment_batch(x, y, spatial=spatial, level_jitter=0.2, time_mask=(6, 10), freq_mask=(8, 6), seed=seed,
+                                          sample_offset=off, return_draws=True)
+    want_x, _, offs = T.random_ups_and_downs(x, None, stddev=0.2, seed=seed, sample_offset=off, return_draws=True)
+    want_y = y
+    if spatial == 'foa':
+        want_x, want_y, d = T.foa_intensity_vec_aug(want_x, y, seed=seed, sample_offset=off, return_draws=True)
+        packed = d['flip'][:, 0] | (d['flip'][:, 1] << 1) | (d['flip'][:, 2] << 2) | (d['swap'] << 3)
+        assert np.array_equal(draws[:, 0].cpu().numpy(), packed)
+    elif spatial == 'acs':
+        want_x, want_y, d = T.acs_aug(want_x, y, seed=seed, sample_offset=off, return_draws=True)
+        assert np.array_equal(draws[:, 0].cpu().numpy(), d['idx'])
+    want_x = want_x.clone()
+    T.mask_batch_(want_x, (6, 10), (8, 6), seed=seed, sample_offset=off)
+    assert np.array_equal(draws[:, 1].cpu().numpy().view(np.float32), offs)       # Box-Muller: device float64 == numpy float64
+    assert torch.equal(got_x, want_x)
+    assert torch.equal(got_y, want_y)
+    assert bool((got_x == 0).any()) and x.data_ptr() != got_x.data_ptr()
+
+
+def test_fused_augment_masks_only_and_transform_wrapper():
+    x = (torch.rand(8, 300, 64, 7) + 1.0).cuda()
+    a, _ = T.augment_batch(x, None, time_mask=(24, 1), freq_mask=(16, 1), seed=3, sample_offset=16)
+    b = x.clone()
+    T.mask_batch_(b, (24, 1), (16, 1), seed=3, sample_offset=16)
+    assert torch.equal(a, b)
+    c, _ = T.augment_batch(x, None, seed=3)                                        # nothing switched on: a copy
+    assert torch.equal(c, x) and c.data_ptr() != x.data_ptr()
+    op = T.batch_augment(spatial='foa', time_mask=(24, 1), freq_mask=(16, 1), seed=9)
+    y = torch.rand(8, 60, 56).cuda()
+    x1, y1 = op(x, y)
+    x2, y2 = op(x, y)
+    assert not torch.equal(x1 == 0, x2 == 0)                                       # the running sample index advances
+    want, wy = T.augment_batch(x, y, spatial='foa', time_mask=(24, 1), freq_mask=(16, 1), seed=9, sample_offset=8)
+    assert torch.equal(x2, want) and torch.equal(y2, wy)
+    with pytest.raises(ValueError):
+        T.augment_batch(x, y, spatial='acs')                                       # acs needs 17 channels
