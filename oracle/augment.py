@@ -90,3 +90,17 @@ def acs_aug_ref(x, y, idx):
     x = np.concatenate([x[..., :1], foa_x, iv, mic_x, gcc], -1)
     y4 = np.concatenate([y4[..., :-3, :], cart], -2)
     return x.astype(np.float32), y4.reshape(y.shape).astype(np.float32)
+
+
+def level_offsets_ref(seed, first_sample, n, stddev, stream_id=0x102):
+    """random_ups_and_downs (reference trainv2.py:120-124) as the product draws it: one N(0, stddev^2) float32 per global sample
+    index -- Box-Muller in float64 on Philox4x32-10 words 0, 1 of counter (lo32(sample), hi32(sample), stream_id, 0), key = seed."""
+    from oracle.tf_random import philox4x32_10
+    out = np.empty(n, dtype=np.float32)
+    stddev = float(np.float32(stddev))               # the C ABI carries the standard deviation as a float
+    for i in range(n):
+        s = first_sample + i
+        w = philox4x32_10((s & 0xFFFFFFFF, s >> 32, stream_id, 0), (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+        u1, u2 = (w[0] + 0.5) / 4294967296.0, (w[1] + 0.5) / 4294967296.0
+        out[i] = stddev * np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    return out

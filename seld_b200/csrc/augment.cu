@@ -97,6 +97,7 @@ struct AugArgs {
     const float* x_in;
     float* x_out;
     unsigned T, F, C;
+    int f_shift;              // log2(F) when F is a power of two, else -1
     int spatial;
     float level_stddev;
     int period, n_chunks;
@@ -105,7 +106,7 @@ struct AugArgs {
     int* draws_out;           // [B][2]: packed spatial draw, level offset bits
 };
 
-// grid = (position blocks, B); one thread = one (t, f) position = C contiguous floats
+// grid = (work blocks, B)
 template <int CT>            // compile-time channel count (0: runtime a.C)
 __global__ void __launch_bounds__(256) augment_kernel(AugArgs a) {
     extern __shared__ unsigned char sm[];
@@ -149,25 +150,45 @@ __global__ void __launch_bounds__(256) augment_kernel(AugArgs a) {
     const float* src = a.x_in + b * (unsigned long long)n_pos * C;
     float* dst = a.x_out + b * (unsigned long long)n_pos * C;
     const float off = s_aug.offset;
-    for (unsigned o = blockIdx.x * blockDim.x + threadIdx.x; o < n_pos; o += gridDim.x * blockDim.x) {
-        const unsigned t = o / a.F, f = o - t * a.F;
-        const bool keep = keep_t[t] && keep_f[(a.period > 0 ? t / a.period : 0) * a.F + f];
-        const float* p = src + (unsigned long long)o * C;
-        float* q = dst + (unsigned long long)o * C;
-        if constexpr (CT > 0) {
+    if constexpr (CT > 0 && CT <= 10) {
+        // one thread = one (t, f) position = CT contiguous floats (a warp covers 32 * CT contiguous floats; CT loads in flight)
+        for (unsigned o = blockIdx.x * blockDim.x + threadIdx.x; o < n_pos; o += gridDim.x * blockDim.x) {
+            const unsigned t = o / a.F, f = o - t * a.F;
+            const bool keep = keep_t[t] && keep_f[(t / a.period) * a.F + f];
+            const float* p = src + (unsigned long long)o * CT;
+            float* q = dst + (unsigned long long)o * CT;
             float r[CT];
 #pragma unroll
-            for (int c = 0; c < CT; ++c) {                    // the C sources of a position share one or two cache lines
+            for (int c = 0; c < CT; ++c) {                    // the sources of a position share one or two cache lines
                 const int sc = s_aug.x_src[c];
                 r[c] = s_aug.x_sgn[c] * (p[sc] + (sc < 4 ? off : 0.f));
             }
 #pragma unroll
             for (int c = 0; c < CT; ++c) q[c] = keep ? r[c] : r[c] * 0.0f;
-        } else {
-            for (unsigned c = 0; c < C; ++c) {
-                const int sc = s_aug.x_src[c];
-                const float r = s_aug.x_sgn[c] * (p[sc] + (sc < 4 ? off : 0.f));
-                q[c] = keep ? r : r * 0.0f;
+        }
+    } else {
+        // wide rows (acs_aug: 17 channels): one thread = one element, consecutive lanes on consecutive floats, four independent
+        // loads in flight per thread
+        const unsigned n_el = n_pos * C, stride = gridDim.x * blockDim.x;
+        constexpr int UN = 4;
+        for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n_el; e0 += UN * stride) {
+            float r[UN];
+            bool keep[UN];
+#pragma unroll
+            for (int k = 0; k < UN; ++k) {
+                const unsigned e = e0 + k * stride;
+                if (e < n_el) {
+                    const unsigned o = e / C, c = e - o * C;
+                    const unsigned t = a.f_shift >= 0 ? (o >> a.f_shift) : o / a.F, f = o - t * a.F;
+                    const int sc = s_aug.x_src[c];
+                    r[k] = s_aug.x_sgn[c] * (src[(unsigned long long)o * C + sc] + (sc < 4 ? off : 0.f));
+                    keep[k] = keep_t[t] && keep_f[(t / a.period) * a.F + f];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < UN; ++k) {
+                const unsigned e = e0 + k * stride;
+                if (e < n_el) dst[e] = keep[k] ? r[k] : r[k] * 0.0f;
             }
         }
     }
@@ -222,6 +243,8 @@ extern "C" int seld_augment_batch(const float* x_in_dev, float* x_out_dev, int64
     AugArgs a;
     a.x_in = x_in_dev; a.x_out = x_out_dev;
     a.T = (unsigned)t; a.F = (unsigned)f; a.C = (unsigned)n_chan;
+    a.f_shift = -1;
+    for (int sh = 0; sh < 31; ++sh) if ((1ll << sh) == f) a.f_shift = sh;
     a.spatial = spatial; a.level_stddev = level_stddev;
     if (time_n + freq_n == 0) period = (int)t;               // no masks: one chunk
     a.period = period;
@@ -231,8 +254,9 @@ extern "C" int seld_augment_batch(const float* x_in_dev, float* x_out_dev, int64
     a.draws_out = draws_out_dev;
     const size_t smem = ((a.T + 15u) & ~15u) + (size_t)a.n_chunks * a.F;
     if (smem > 160 * 1024) { set_error("augment: time axis too long for shared memory"); return SELD_EUNSUPPORTED; }
-    const long long n_pos = t * f;
-    long long bx = (n_pos + 255) / 256;
+    if (t * f * n_chan >= (1ll << 31)) { set_error("sample too large (2^31 elements)"); return SELD_EUNSUPPORTED; }
+    const long long n_items = (n_chan == 7 || n_chan == 10) ? t * f : (t * f * n_chan + 3) / 4;     // positions | 4-element groups
+    long long bx = (n_items + 255) / 256;
     const long long cap = ((long long)device_sm_count() * 16 + n_samples - 1) / n_samples;
     if (bx > cap) bx = cap < 1 ? 1 : cap;
     dim3 grid((unsigned)bx, (unsigned)n_samples);

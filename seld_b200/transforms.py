@@ -176,45 +176,24 @@ def mask_batch_(x, time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, 
 STREAM_LEVEL_JITTER = 0x102
 
 
-def _level_offsets(n, stddev, seed, sample_offset):
-    """One N(0, stddev^2) float32 per sample: Box-Muller (float64) on Philox words 0, 1 of (sample, STREAM_LEVEL_JITTER)."""
-    from . import philox
-    seed, first = _draw_seed(n, seed, sample_offset)
-    w = philox.sample_words(seed, first, n, STREAM_LEVEL_JITTER).astype(np.float64)
-    u1, u2 = (w[:, 0] + 0.5) / 4294967296.0, (w[:, 1] + 0.5) / 4294967296.0
-    return (stddev * np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)).astype(np.float32)
-
-
-def _offset_copy(x, offsets, n_first):
-    """New tensor: x[b, ..., c] + offsets[b] for c < n_first (one pass; also the copy the masks need)."""
-    _lib.require_device()
-    xs = x.to(dtype=torch.float32).contiguous()
-    out = torch.empty_like(xs)
-    off = torch.as_tensor(np.ascontiguousarray(offsets, dtype=np.float32), device=xs.device)
-    b, c = xs.shape[0], xs.shape[-1]
-    with torch.cuda.device(xs.device):
-        _lib.check(_lib.load().seld_channel_offset(_lib.ptr(xs), _lib.ptr(out), b, xs[0].numel() // c, c, int(n_first),
-                                                   _lib.ptr(off), _lib.current_stream_ptr()))
-    return out
-
-
 def random_ups_and_downs(x, y, stddev=0.2, seed=None, sample_offset=None, return_draws=False):
     """reference trainv2.py:120-124: add ONE N(0, 0.2^2) scalar to channels [:4] (the log-mel block).  The reference maps
-    it over single samples [T, F, C]; here x may also be a batch [B, T, F, C] (one independent scalar per sample)."""
+    it over single samples [T, F, C]; here x may also be a batch [B, T, F, C] (one independent scalar per sample).
+    The scalar is drawn on the device: Box-Muller in float64 on Philox words 0, 1 of (seed, sample, STREAM_LEVEL_JITTER)."""
     xt = torch.as_tensor(x)
     single = xt.dim() == 3
+    _lib.require_device()
     xb = (xt.unsqueeze(0) if single else xt).cuda()
-    offs = _level_offsets(xb.shape[0], stddev, seed, sample_offset)
-    out = _offset_copy(xb, offs, min(4, xb.shape[-1]))
+    out, _, draws = augment_batch(xb, None, level_jitter=stddev, seed=seed, sample_offset=sample_offset, return_draws=True)
     out = out[0] if single else out
-    return (out, y, offs) if return_draws else (out, y)
+    return (out, y, draws[:, 1].cpu().numpy().view(np.float32).copy()) if return_draws else (out, y)
 
 
 def sample_masks(time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, level_jitter=None):
     """The reference's per-sample transforms (train.py:157-160: ``mask(x, axis=-3, max_mask_size=24, n_mask=1)`` then
     ``mask(x, axis=-2, max_mask_size=16)``; trainv2.py:134-138 puts ``random_ups_and_downs`` in front: ``level_jitter=0.2``)
     as ONE batched transform for ``data_loader.seldnet_data_to_dataloader``: ``(x [B, T, F, C], y) -> (new x, y)``,
-    independent draws per sample; the level jitter rides on the copy the masks need, then one fused masking launch."""
+    independent draws per sample; jitter, copy and both mask axes are ONE launch (seld_augment_batch)."""
     state = {'next_sample': 0}          # with an explicit seed: this transform's own running sample index, so that every
     lock = threading.Lock()             # batch (and every epoch) draws fresh bands, reproducibly
 
@@ -224,11 +203,7 @@ def sample_masks(time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, le
             with lock:
                 first = state['next_sample']
                 state['next_sample'] += int(x.shape[0])
-        if level_jitter:
-            out = _offset_copy(x, _level_offsets(x.shape[0], float(level_jitter), seed, first), min(4, x.shape[-1]))
-        else:
-            out = x.clone(memory_format=torch.contiguous_format)
-        mask_batch_(out, time_mask, freq_mask, period=period, seed=seed, sample_offset=first)
+        out, _ = augment_batch(x, None, None, level_jitter, time_mask, freq_mask, period, seed, first)      # one launch
         return out, y
     op.batched = True
     return op
@@ -328,35 +303,6 @@ def mic_gcc_perm(mic_perm):
     return torch.from_numpy(out) if isinstance(mic_perm, torch.Tensor) else out
 
 
-def _pack_table(perm, sign):
-    """[B, C] source channels + signs (+1 / -1) -> int32 table of seld_channel_remap (bit 31 = negate)."""
-    t = np.asarray(perm, dtype=np.int64) | np.where(np.asarray(sign) < 0, 1 << 31, 0)
-    return t.astype(np.uint32).view(np.int32)
-
-
-def _remap_pair(xs, ys, x_tab, y_tab):
-    """Apply the per-sample tables to features [B, ..., C] and label coordinates [B, T, 4 * n_classes]; new tensors."""
-    b, cx = xs.shape[0], xs.shape[-1]
-    n_cls = ys.shape[-1] // 4
-    tab = torch.as_tensor(np.ascontiguousarray(np.concatenate([x_tab.ravel(), y_tab.ravel()])), device=xs.device)   # one H2D
-    xo, yo = torch.empty_like(xs), torch.empty_like(ys)
-    lib = _lib.load()
-    with torch.cuda.device(xs.device):
-        st = _lib.current_stream_ptr()
-        _lib.check(lib.seld_channel_remap(_lib.ptr(xs), _lib.ptr(xo), b, int(np.prod(xs.shape[1:-1])), cx, 1, tab.data_ptr(), st))
-        _lib.check(lib.seld_channel_remap(_lib.ptr(ys), _lib.ptr(yo), b, int(np.prod(ys.shape[1:-1])), 4, n_cls,
-                                          tab.data_ptr() + 4 * b * cx, st))
-    return xo, yo
-
-
-def _aug_inputs(x, y):
-    _lib.require_device()
-    dev = torch.device('cuda', torch.cuda.current_device())
-    xs = torch.as_tensor(x).to(device=dev, dtype=torch.float32).contiguous()
-    ys = torch.as_tensor(y).to(device=dev, dtype=torch.float32).contiguous()
-    return xs, ys
-
-
 def _draw_seed(n, seed, sample_offset):
     if seed is None:
         seed, first = _take_samples(n)
@@ -364,66 +310,37 @@ def _draw_seed(n, seed, sample_offset):
     return int(seed) & (2 ** 64 - 1), 0 if sample_offset is None else int(sample_offset)
 
 
+def _aug_inputs(x, y):
+    _lib.require_device()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    xs = torch.as_tensor(x)
+    ys = torch.as_tensor(y)
+    xs = xs if xs.is_cuda else xs.to(dev)
+    return xs.to(torch.float32).contiguous(), ys.to(device=xs.device, dtype=torch.float32).contiguous()
+
+
 def foa_intensity_vec_aug(x, y, seed=None, sample_offset=None, return_draws=False):
     """reference transforms.py:78-114 for x [B, T, F, 7], y [B, T, 4*n_classes]: per sample, random sign flips of the
-    three intensity / coordinate axes and a random x<->y... swap ([0,1,2] or the reference's [2,1,0] channel order),
+    three intensity / coordinate axes and a random x<->z swap ([0,1,2] or the reference's [2,1,0] channel order),
     applied consistently to the FOA channels 1..3, the intensity vectors 4..6 and the label coordinates.
-    Draws: Philox word 0..2 & 1 = flips, word 3 & 1 = swap, per global sample index."""
-    from . import philox
+    Draws (on the device): Philox words 0..2 & 1 = flips, word 3 & 1 = swap, per global sample index."""
     xs, ys = _aug_inputs(x, y)
-    b = xs.shape[0]
-    if xs.shape[-1] != 7 or ys.shape[-1] % 4:
+    if xs.dim() != 4 or xs.shape[-1] != 7 or ys.shape[-1] % 4:
         raise ValueError('x must be [B, T, F, 7] and y [B, T, 4*n_classes]')
-    seed, first = _draw_seed(b, seed, sample_offset)
-    w = philox.sample_words(seed, first, b, STREAM_IV_AUG)
-    flip = (w[:, :3] & 1).astype(np.int64)                              # tf.random.uniform([B, 3], 0, 2)
-    swap = (w[:, 3] & 1).astype(np.int64)                               # tf.random.uniform([B, 1], maxval=2)
-    perm = np.stack([2 * swap, np.ones_like(swap), 2 - 2 * swap], 1)    # [p, 1, 2-p], p in {0, 2}        (:100-101)
-    check = (perm != np.array([0, 1, 2])).sum(1, keepdims=True)
-    feat_perm = (perm + check) % 3                                       # (:103-104)
-    sgn = 1 - 2 * flip                                                   # flips happen BEFORE the gather (:96-97)
-    x_perm = np.tile(np.arange(7), (b, 1))
-    x_sign = np.ones((b, 7))
-    x_perm[:, 1:4] = 1 + perm                                            # FOA channels follow `perm`     (:109)
-    x_perm[:, 4:7] = 4 + feat_perm                                       # IV channels follow `feat_perm` (:106)
-    x_sign[:, 4:7] = np.take_along_axis(sgn, feat_perm, 1)
-    y_perm = np.tile(np.arange(4), (b, 1))
-    y_sign = np.ones((b, 4))
-    y_perm[:, 1:4] = 1 + feat_perm                                       # label x, y, z                   (:107)
-    y_sign[:, 1:4] = np.take_along_axis(sgn, feat_perm, 1)
-    xs, ys = _remap_pair(xs, ys, _pack_table(x_perm, x_sign), _pack_table(y_perm, y_sign))
-    return (xs, ys, {'flip': flip, 'swap': swap}) if return_draws else (xs, ys)
+    xo, yo, draws = augment_batch(xs, ys, spatial='foa', seed=seed, sample_offset=sample_offset, return_draws=True)
+    if not return_draws:
+        return xo, yo
+    w = draws[:, 0].cpu().numpy().astype(np.int64)
+    return xo, yo, {'flip': np.stack([w & 1, (w >> 1) & 1, (w >> 2) & 1], 1), 'swap': (w >> 3) & 1}
 
 
 def acs_aug(x, y, seed=None, sample_offset=None, return_draws=False):
     """reference transforms.py:155-199, audio channel swapping for x [B, T, F, 17] (4 FOA log-mel, 3 IV, 4 MIC log-mel,
     6 GCC) and y [B, T, 4*n_classes]: one of the 8 rotations / reflections of `channel_list` per sample, applied to
     the FOA channels, intensity vectors (with signs), microphone channels, GCC pair channels and label coordinates.
-    Draw: Philox word 0 % 8 per global sample index."""
-    from . import philox
+    Draw (on the device): Philox word 0 % 8 per global sample index."""
     xs, ys = _aug_inputs(x, y)
-    b = xs.shape[0]
-    if xs.shape[-1] != 17 or ys.shape[-1] % 4:
+    if xs.dim() != 4 or xs.shape[-1] != 17 or ys.shape[-1] % 4:
         raise ValueError('x must be [B, T, F, 17] and y [B, T, 4*n_classes]')
-    seed, first = _draw_seed(b, seed, sample_offset)
-    idx = (philox.sample_words(seed, first, b, STREAM_ACS_AUG)[:, 0] % 8).astype(np.int64)
-    table = np.array(channel_list, dtype=np.int64)                      # [8, 2, 4]
-    mic_flip = table[idx, 0, :]
-    foa_flip = table[idx, 1, 1:]
-    foa_sign = np.sign(foa_flip)
-    foa_perm = foa_sign * foa_flip - 1                                   # (:176)
-    check = (foa_perm != np.array([0, 1, 2])).sum(1, keepdims=True)
-    feat_perm = (foa_perm + check) % 3                                   # (:179)
-    x_perm = np.tile(np.arange(17), (b, 1))
-    x_sign = np.ones((b, 17))
-    x_perm[:, 1:4] = 1 + foa_perm                                        # (:180)
-    x_perm[:, 4:7] = 4 + feat_perm
-    x_sign[:, 4:7] = foa_sign                                            # sign applied AFTER the gather (:182)
-    x_perm[:, 7:11] = 7 + mic_flip                                       # (:190)
-    x_perm[:, 11:17] = 11 + np.asarray(mic_gcc_perm(mic_flip))           # (:188-189)
-    y_perm = np.tile(np.arange(4), (b, 1))
-    y_sign = np.ones((b, 4))
-    y_perm[:, 1:4] = 1 + feat_perm                                       # (:183)
-    y_sign[:, 1:4] = foa_sign
-    xs, ys = _remap_pair(xs, ys, _pack_table(x_perm, x_sign), _pack_table(y_perm, y_sign))
-    return (xs, ys, {'idx': idx}) if return_draws else (xs, ys)
+    xo, yo, draws = augment_batch(xs, ys, spatial='acs', seed=seed, sample_offset=sample_offset, return_draws=True)
+    return (xo, yo, {'idx': draws[:, 0].cpu().numpy().astype(np.int64)}) if return_draws else (xo, yo)

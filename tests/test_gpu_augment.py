@@ -157,3 +157,12 @@ def test_fused_augment_masks_only_and_transform_wrapper():
     assert torch.equal(x2, want) and torch.equal(y2, wy)
     with pytest.raises(ValueError):
         T.augment_batch(x, y, spatial='acs')                                       # acs needs 17 channels
+
+
+def test_device_level_jitter_matches_its_restatement():
+    """Box-Muller in float64 on the device vs numpy: the same float32 up to the last bit of a float64 transcendental."""
+    x = torch.zeros(512, 1, 1, 7, device='cuda')
+    out, _, offs = T.random_ups_and_downs(x, None, stddev=0.2, seed=77, sample_offset=1000, return_draws=True)
+    want = A.level_offsets_ref(77, 1000, 512, 0.2)
+    assert offs.dtype == np.float32 and np.abs(offs - want).max() <= 1.2e-7 and (offs == want).mean() > 0.9
+    assert np.array_equal(out[:, 0, 0, 0].cpu().numpy(), offs) and float(out[..., 4:].abs().max()) == 0.0
