@@ -41,7 +41,13 @@ extern "C" {
 #define SELD_LAYOUT_INTERLEAVED_LC 1 /* wav[clip][sample][chan]  (one 128-bit load = one time step of 4 channels) */
 
 #define SELD_RNG_PHILOX_COUNTER 0   /* Philox4x32-10, counter = (sample, axis slot, chunk, 2*mask+draw) */
-#define SELD_RNG_TF_EAGER_COMPAT 1  /* TensorFlow-2 eager op-seed stream (reproduces transforms_test.py:8-30) */
+#define SELD_RNG_TF_EAGER_COMPAT 1  /* TensorFlow-2 eager op-seed stream (reproduces transforms_test.py:8-30); op_seed2 index
+                                      ((sample * n_chunks + chunk) * (time_n + freq_n) + mask) * 2 + draw */
+#define SELD_RNG_TF_EAGER_TWO_PASS 2 /* the same stream in the order of TWO reference calls per sample -- mask(axis=-3) then
+                                      mask(axis=-2), train.py:157-160: all time draws of all chunks, then all frequency draws:
+                                      time  sample * S + (chunk * time_n + mask) * 2 + draw
+                                      freq  sample * S + n_chunks * time_n * 2 + (chunk * freq_n + mask) * 2 + draw,
+                                      S = n_chunks * (time_n + freq_n) * 2 */
 
 #define SELD_DTYPE_F32 0
 #define SELD_DTYPE_F64 1

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get('SELD_B200_LIB') or os.path.join(_HERE, 'libseld_b200.
 
 MODE_FOA, MODE_MIC, MODE_FOA_TF = 0, 1, 2
 LAYOUT_PLANAR_CL, LAYOUT_INTERLEAVED_LC = 0, 1
-RNG_PHILOX_COUNTER, RNG_TF_EAGER_COMPAT = 0, 1
+RNG_PHILOX_COUNTER, RNG_TF_EAGER_COMPAT, RNG_TF_EAGER_TWO_PASS = 0, 1, 2
 DTYPE_CODES = {'float32': 0, 'float64': 1, 'float16': 2, 'bfloat16': 3, 'int32': 4, 'int64': 5, 'int16': 6, 'uint8': 7}
 
 _c = ctypes

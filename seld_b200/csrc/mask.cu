@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256) mask_kernel(MaskArgs a) {
             u_size = philox4x32_10_first(uint32_t(gs), uint32_t(gs >> 32), uint32_t(chunk), c3, k0, k1);
             u_off = philox4x32_10_first(uint32_t(gs), uint32_t(gs >> 32), uint32_t(chunk), c3 | 1u, k0, k1);
         } else {
-            const long long base = ((sample * a.n_chunks + chunk) * n_masks + m) * 2;
+            long long base = ((sample * a.n_chunks + chunk) * n_masks + m) * 2;
+            if (a.rng_mode == SELD_RNG_TF_EAGER_TWO_PASS)
+                base = sample * (long long)a.n_chunks * n_masks * 2 +
+                       (is_time ? ((long long)chunk * a.time_n + mi) * 2 : ((long long)a.n_chunks * a.time_n + (long long)chunk * a.freq_n + mi) * 2);
             const unsigned long long s2a = (unsigned long long)a.op_seed2[base], s2b = (unsigned long long)a.op_seed2[base + 1];
             const uint32_t k0 = uint32_t(a.seed), k1 = uint32_t(a.seed >> 32);
             u_size = philox4x32_10_first(0u, 0u, uint32_t(s2a), uint32_t(s2a >> 32), k0, k1);
@@ -139,8 +142,11 @@ extern "C" int seld_mask(void* x_dev, int dtype, int64_t n_samples, int64_t t, i
     if (t % period != 0) { set_error("(spec time length / period)' rest must be 0"); return SELD_EINVAL; }
     if (time_n > 0 && time_max > period) { set_error("time max_mask_size exceeds the period"); return SELD_EINVAL; }
     if (freq_n > 0 && freq_max > f) { set_error("freq max_mask_size exceeds the axis length"); return SELD_EINVAL; }
-    if (rng_mode == SELD_RNG_TF_EAGER_COMPAT && op_seed2_dev == nullptr) { set_error("TF_EAGER_COMPAT needs op_seed2"); return SELD_EINVAL; }
-    if (rng_mode != SELD_RNG_TF_EAGER_COMPAT && rng_mode != SELD_RNG_PHILOX_COUNTER) { set_error("bad rng_mode"); return SELD_EINVAL; }
+    if (rng_mode != SELD_RNG_TF_EAGER_COMPAT && rng_mode != SELD_RNG_TF_EAGER_TWO_PASS && rng_mode != SELD_RNG_PHILOX_COUNTER) {
+        set_error("bad rng_mode");
+        return SELD_EINVAL;
+    }
+    if (rng_mode != SELD_RNG_PHILOX_COUNTER && op_seed2_dev == nullptr) { set_error("the TF-eager modes need op_seed2"); return SELD_EINVAL; }
     const int num_sms = device_sm_count();
     MaskArgs a;
     a.x = x_dev;

@@ -156,7 +156,10 @@ def mask_batch_(x, time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, 
     """Fused in-place masking of a CUDA batch ``x[B, T, F, C]``: per sample and per ``period``-frame chunk,
     ``time_mask = (max_size, n)`` bands of frames then ``freq_mask = (max_size, n)`` bands of mel bins -- the
     ``sample_transforms`` of reference train.py:157-160 (24x1, 16x1) / trainv2.py:136-137 (6x10, 8x6) in one pass.
-    Draws depend only on (seed, sample_offset + b, axis, chunk, mask, draw)."""
+    Draws depend only on (seed, sample_offset + b, axis, chunk, mask, draw).
+    After ``set_seed(s)`` (and with ``seed=None``) the bands follow TensorFlow-2's eager stream instead, in the order the
+    reference's two calls per sample consume it -- ``mask(x, axis=-3, ...)`` then ``mask(x, axis=-2, ...)``, sample after
+    sample: all time draws of all chunks, then all frequency draws -- still as ONE launch."""
     if not (isinstance(x, torch.Tensor) and x.is_cuda and x.is_contiguous() and x.dim() == 4):
         raise ValueError('x must be a contiguous CUDA tensor [B, T, F, C]')
     b, t, f, c = x.shape
@@ -164,6 +167,13 @@ def mask_batch_(x, time_mask=(24, 1), freq_mask=(16, 1), period=100, seed=None, 
         raise ValueError("(spec time length / period)' rest must be 0")
     tm, tn = time_mask if time_mask else (0, 0)
     fm, fn = freq_mask if freq_mask else (0, 0)
+    tf = getattr(_state, 'tf', None)
+    if seed is None and tf is not None and b > 0 and (tn + fn) > 0:
+        n_chunks = t // period
+        seeds = [tf.next_seed2() for _ in range(b * n_chunks * (int(tn) + int(fn)) * 2)]
+        op_seed2 = torch.tensor(seeds, dtype=torch.int64, device=x.device)
+        return _launch(x, b, t, 1, f, c, int(period), tm, int(tn), fm, int(fn), tf.kernel_seed(), 0, _lib.RNG_TF_EAGER_TWO_PASS,
+                       op_seed2, return_draws)
     if seed is None:
         seed, first = _take_samples(b)
         sample_offset = first if sample_offset is None else sample_offset

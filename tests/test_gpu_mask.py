@@ -106,3 +106,24 @@ def test_unseeded_stream_is_counter_based_and_advances():
     T.set_counter_seed(42, 0)
     assert torch.equal(T.mask(x, 0, 24), a) and torch.equal(T.mask(x, 0, 24), b)
     assert a.is_cuda and torch.equal(x, x)                            # input untouched, result stays on the GPU
+
+
+@pytest.mark.parametrize('params', [((24, 1), (16, 1)), ((6, 10), (8, 6))])
+def test_fused_batch_mask_follows_the_tf_eager_stream_of_two_reference_calls(params):
+    """After set_seed(s), ONE fused launch over a batch == the reference's eager sequence per sample: mask(x, axis=-3) -- all
+    chunks' time draws -- then mask(x, axis=-2) -- all chunks' frequency draws (train.py:157-160), sample after sample."""
+    from oracle.masking import mask_ref
+    from oracle.tf_random import TFEagerRandom
+    from seld_b200 import transforms as T
+    (tm, tn), (fm, fn) = params
+    x = np.random.default_rng(3).standard_normal((5, 300, 64, 7)).astype(np.float32)
+    r = TFEagerRandom(404)
+    want = np.empty_like(x)
+    for s in range(x.shape[0]):
+        a, _ = mask_ref(x[s], -3, lambda ch: r.uniform_int, tm, 100, tn)
+        want[s], _ = mask_ref(a, -2, lambda ch: r.uniform_int, fm, 100, fn)
+    T.set_seed(404)
+    y = torch.from_numpy(x).cuda()
+    T.mask_batch_(y, (tm, tn), (fm, fn))
+    T.set_seed(None)
+    assert np.array_equal(y.cpu().numpy(), want)
