@@ -194,6 +194,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of one CUDA graph per step')
     ap.add_argument('--no-mic', action='store_true')
     ap.add_argument('--no-weak', action='store_true')
+    ap.add_argument('--no-peer', action='store_true', help='skip the peer-memory all-reduce variant (N > 1)')
     ap.add_argument('--no-config5', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -243,10 +244,11 @@ def main():
     if rank == 0:
         sampler.start()
 
-    def measure(mode, indices, steps):
-        """Device-resident job over this rank's clips -> dict (times are max over ranks)."""
+    def measure(mode, indices, steps, peer=False):
+        """Device-resident job over this rank's clips -> dict (times are max over ranks).  peer: the statistics all-reduce as this
+        package's one-launch exchange over NVLink peer memory instead of NCCL."""
         wav = make_shard(mode, indices)
-        step = pipeline.DatasetStep(wav, SR, mode=mode, n_mels=N_MELS, t_out=T_OUT, layout=args.layout, **PROD)
+        step = pipeline.DatasetStep(wav, SR, mode=mode, n_mels=N_MELS, t_out=T_OUT, layout=args.layout, peer_allreduce=peer, **PROD)
         for _ in range(args.warmup):
             step.run()
         barrier()
@@ -321,6 +323,24 @@ def main():
     for mode in modes:
         mine = sharding.shard_indices(total, rank, world)
         res, mean, std = measure(mode, list(mine), args.steps)
+        res['allreduce'] = {'used': 'nccl', 'nccl_ms_per_step': res['ms_graph'] or res['ms_eager']}
+        if world > 1 and not args.no_peer:
+            # the same job with the statistics all-reduce as ONE kernel over NVLink peer memory; the faster one is the headline
+            try:
+                res_p, mean_p, std_p = measure(mode, list(mine), args.steps, peer=True)
+                ms_p = res_p['ms_graph'] or res_p['ms_eager']
+                same = bool(torch.equal(mean_p, mean) and torch.equal(std_p, std))
+                info = {'nccl_ms_per_step': res['allreduce']['nccl_ms_per_step'], 'peer_ms_per_step': ms_p,
+                        'nccl_stats_stage_ms': res['stage_ms']['stats+allreduce'], 'peer_stats_stage_ms': res_p['stage_ms']['stats+allreduce'],
+                        'peer_equals_nccl_bitwise': same}
+                if ms_p < info['nccl_ms_per_step']:
+                    res, mean, std = res_p, mean_p, std_p
+                    info['used'] = 'peer (seld_stats_peer_allreduce: one launch over NVLink peer memory)'
+                else:
+                    info['used'] = 'nccl'
+                res['allreduce'] = info
+            except Exception as exc:           # noqa: BLE001  (no symmetric memory on this box, ...)
+                res['allreduce']['peer_error'] = str(exc).splitlines()[0][:200]
         ms = res['ms_graph'] or res['ms_eager']
         res['value'] = total * CLIP_HOURS / (ms / 1000.0)
         res['ms_per_step'] = ms
@@ -436,6 +456,7 @@ def main():
                 'data': 'synthetic', 'config': workload_config(args, 'foa', total, world),
                 'graph': {'used': foa['ms_graph'] is not None, 'ms_per_step_graph': foa['ms_graph'], 'ms_per_step_eager': foa['ms_eager'],
                           'error': foa['graph_error']},
+                'allreduce': foa.get('allreduce'),
                 'roofline': dict(foa['roofline'], stage_ms=foa['stage_ms']), 'cpu_baseline': cpu,
                 'e2e': e2e.get('foa'), 'gpu_launches': int(round(foa['launches_per_step'] * args.steps)),
                 'gpu_launches_per_step': foa['launches_per_step'], 'clocks': clocks}
@@ -443,7 +464,7 @@ def main():
             mic = out['mic']
             line['mic'] = {'value': mic['value'], 'unit': UNIT, 'ms_per_step': mic['ms_per_step'], 'ms_per_step_eager': mic['ms_eager'],
                            'roofline': dict(mic['roofline'], stage_ms=mic['stage_ms']), 'e2e': e2e.get('mic'),
-                           'gpu_launches_per_step': mic['launches_per_step'],
+                           'gpu_launches_per_step': mic['launches_per_step'], 'allreduce': mic.get('allreduce'),
                            'config': workload_config(args, 'mic', total, world)['workload']}
             both_ms = foa['ms_per_step'] + mic['ms_per_step']
             alg = total * (ALG_BYTES['foa'] + ALG_BYTES['mic'] + 2 * 4 * T_OUT * N_MELS * 17)

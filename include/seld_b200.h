@@ -169,6 +169,17 @@ SELD_API int64_t seld_stats_workspace_doubles(int n_mels, int n_ch);
 SELD_API int seld_stats(int n_mels, int n_ch, const float* feat_dev, const uint32_t* clip_max_key_dev, int n_clips, int t_out,
                int t_valid, float top_db, double* workspace_dev, double* acc_dev, void* stream);
 /* mean = sum/n_rows, std = sqrt(max(sumsq/n_rows - mean^2, 0)) (population, ddof 0) -> float32 [n_mels][C]. */
+/*
+ * The statistics all-reduce as ONE kernel over NVLink peer memory instead of a library collective (<= 1 281 doubles,
+ * latency bound).  Every rank owns an exchange buffer of seld_stats_peer_buffer_bytes(n_values) bytes, zero-initialised once, that
+ * ALL ranks can address (CUDA IPC / torch symmetric memory); peer_base_dev[world] holds the base address of every rank's buffer as
+ * seen from this rank.  acc_dev[n_values] (n_values = 2 * n_mels * C + 1): in = this rank's sums, out = the sums over all ranks, added
+ * in rank order on every rank (bit-identical everywhere).  All ranks must enqueue the call the same number of times (it contains
+ * a cross-GPU barrier); the epoch counter lives in the buffer, so the launch can sit in a replayed CUDA graph.
+ */
+SELD_API int64_t seld_stats_peer_buffer_bytes(int n_values);
+SELD_API int seld_stats_peer_allreduce(const uint64_t* peer_base_dev, int rank, int world, int n_values, double* acc_dev, void* stream);
+
 SELD_API int seld_stats_finish(int n_mels, int n_ch, const double* acc_dev, float* mean_dev, float* std_dev, void* stream);
 
 /*

@@ -34,6 +34,8 @@ SIGNATURES = {
     'seld_extract_pcm16': (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i64, _vp]),
     'seld_clip_max_decode': (_i, [_vp, _i, _vp, _vp]),
     'seld_finalize': (_i, [_i, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _f, _vp, _vp]),
+    'seld_stats_peer_buffer_bytes': (_i64, [_i]),
+    'seld_stats_peer_allreduce': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'seld_stats_workspace_doubles': (_i64, [_i, _i]),
     'seld_stats': (_i, [_i, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     'seld_stats_finish': (_i, [_i, _i, _vp, _vp, _vp, _vp]),

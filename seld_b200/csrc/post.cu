@@ -186,6 +186,65 @@ __global__ void stats_fold_kernel(const double* __restrict__ partials, int n_blo
     if (i == 0) acc[n2] += n_rows;
 }
 
+// ------------------------------------------------------------------ one-shot all-reduce over NVLink peer memory
+// The path's only collective: the per-bin {sum, sum of squares, count} vector, <= 1 281 doubles.  NCCL spends ~70 us
+// on it inside an 8-GPU step of 1.5 ms (profiles/r2_bench_n8_a.json); this kernel does it in one launch over buffers every rank
+// can address (torch symmetric memory / cudaIpc -- the caller hands in the peer base pointers):
+//   publish   acc -> own exchange slot (parity of a device-side epoch counter), system-scope fence
+//   signal    flag[my rank] := epoch in EVERY rank's buffer (st.release.sys over NVLink)
+//   wait      until every rank's flag in the own buffer has reached the epoch (ld.acquire.sys)
+//   reduce    sum the W peer slots in RANK ORDER (L1-bypassing loads) -> acc: every rank adds the same numbers in the same order,
+//             so the result is bit-identical on all ranks and run to run
+// Two slots suffice: a rank can only overwrite slot e & 1 at epoch e + 2, and to get there it has passed barrier e + 1, which every
+// peer signals only after it finished reading epoch e.  The epoch lives in device memory, so a captured CUDA graph replays it.
+// Buffer of a rank: [0, 256) flags (uint32 per rank), [256, 264) epoch counter, [512, ...) two slots of n doubles.
+constexpr int kPeerHeaderBytes = 512;
+constexpr int kPeerMaxWorld = 64;
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) stats_peer_allreduce_kernel(const unsigned long long* __restrict__ peer_base, int rank, int world, int n,
+                                                                    double* __restrict__ acc) {
+    __shared__ unsigned s_epoch;
+    __shared__ unsigned long long s_base[kPeerMaxWorld];
+    if (threadIdx.x < world) s_base[threadIdx.x] = peer_base[threadIdx.x];
+    __syncthreads();
+    unsigned char* mine = reinterpret_cast<unsigned char*>(s_base[rank]);
+    if (threadIdx.x == 0) {
+        unsigned* ep = reinterpret_cast<unsigned*>(mine + 256);
+        s_epoch = *ep + 1u;
+        *ep = s_epoch;
+    }
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const size_t slot_off = kPeerHeaderBytes + size_t(epoch & 1u) * n * sizeof(double);
+    double* my_slot = reinterpret_cast<double*>(mine + slot_off);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) my_slot[i] = acc[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        st_release_sys(reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(s_base[threadIdx.x])) + rank, epoch);
+        const unsigned* flag = reinterpret_cast<const unsigned*>(mine) + threadIdx.x;
+        while (int(ld_acquire_sys(flag) - epoch) < 0) { }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double a = 0.0;
+        for (int r = 0; r < world; ++r) a += ld_relaxed_sys_f64(reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(s_base[r]) + slot_off) + i);
+        acc[i] = a;
+    }
+}
+
 // generic (row_len % 4 != 0) fallback: one thread per column, block-strided rows, same fixed-order fold
 __global__ void __launch_bounds__(256) stats_partial_scalar_kernel(const float* __restrict__ x, const unsigned int* __restrict__ keys,
                                                                    long long n_rows, int t_out, int t_valid, int row_len,
@@ -291,6 +350,23 @@ int seld_stats(int n_mels, int n_ch, const float* feat_dev, const uint32_t* clip
     seld::note_launch();
     const int n2 = 2 * row_len;
     stats_fold_kernel<<<(n2 + 127) / 128, 128, 0, st>>>(workspace_dev, blocks, n2, double(n_rows), acc_dev);
+    SELD_CUDA_TRY(cudaGetLastError());
+    seld::note_launch();
+    return SELD_OK;
+}
+
+int64_t seld_stats_peer_buffer_bytes(int n_values) {
+    if (n_values < 1) return SELD_EINVAL;
+    return kPeerHeaderBytes + 2ll * n_values * (int64_t)sizeof(double);
+}
+
+int seld_stats_peer_allreduce(const uint64_t* peer_base_dev, int rank, int world, int n_values, double* acc_dev, void* stream) {
+    if (!peer_base_dev || !acc_dev || n_values < 1 || world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) {
+        set_error("bad argument");
+        return SELD_EINVAL;
+    }
+    stats_peer_allreduce_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long*>(peer_base_dev), rank,
+                                                                                  world, n_values, acc_dev);
     SELD_CUDA_TRY(cudaGetLastError());
     seld::note_launch();
     return SELD_OK;

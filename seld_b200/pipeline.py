@@ -218,13 +218,56 @@ def partial_statistics(feat, clip_max_key=None, t_valid=None, acc=None, top_db=T
     return acc
 
 
-def allreduce_statistics(acc):
+def allreduce_statistics(acc, peer=None):
     """Sum the accumulators over all ranks (no-op without an initialised process group).  This is the path's only
-    collective: 2*64*C + 1 doubles (<= 10.2 KB) over NCCL / NVLink."""
+    collective: 2*64*C + 1 doubles (<= 10.2 KB).  Default: one NCCL all-reduce; with ``peer`` (a PeerStatisticsAllReduce)
+    the package's own one-launch exchange over NVLink peer memory."""
     import torch.distributed as dist
+    if peer is not None:
+        return peer(acc)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
     return acc
+
+
+class PeerStatisticsAllReduce:
+    """The statistics all-reduce as ONE kernel over NVLink peer memory (seld_stats_peer_allreduce, csrc/post.cu): every rank
+    publishes its <= 1 281 doubles into its own exchange buffer, flags all peers, waits for theirs and sums the W slots in rank
+    order (bit-identical on every rank).  The buffers are torch symmetric memory (plumbing: allocation + exchange of the peer
+    addresses); the exchange itself is this package's kernel.  At 75 clips per GPU (BASELINE.json config 4, N = 8) the NCCL
+    call costs ~70 us of a 1.5 ms step."""
+
+    def __init__(self, n_values, device=None, group=None, peer_ptrs=None, rank=None, world=None):
+        import torch.distributed as dist
+        self.n = int(n_values)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        lib = _lib.load()
+        nbytes = int(lib.seld_stats_peer_buffer_bytes(self.n))
+        if peer_ptrs is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            import torch.distributed._symmetric_memory as symm
+            group = group or dist.group.WORLD
+            self.buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.buf.zero_()
+            self.handle = symm.rendezvous(self.buf, group)
+            peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)                       # every buffer is zeroed before anyone's first flag arrives
+        else:
+            if peer_ptrs is None:                     # single rank: its own buffer is the only peer
+                self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+                peer_ptrs = [self.buf.data_ptr()]
+            self.rank = 0 if rank is None else int(rank)
+            self.world = len(peer_ptrs) if world is None else int(world)
+        self.peers = torch.tensor(peer_ptrs, dtype=torch.int64, device=self.device)
+
+    def __call__(self, acc):
+        if not (acc.is_cuda and acc.dtype == torch.float64 and acc.is_contiguous() and acc.numel() == self.n):
+            raise ValueError(f'acc must be a contiguous float64 CUDA tensor of {self.n} values')
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().seld_stats_peer_allreduce(_lib.ptr(self.peers), self.rank, self.world, self.n, _lib.ptr(acc),
+                                                             _lib.current_stream_ptr()))
+        return acc
 
 
 def stats_workspace(n_mels, n_ch, device):
@@ -266,7 +309,7 @@ class DatasetStep:
     75 clips per GPU (BASELINE.json config 4 at N = 8) the step is ~1.5 ms and eight launches plus a collective are a
     visible share of it."""
 
-    def __init__(self, wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', **kwargs):
+    def __init__(self, wav, sample_rate, mode='foa', n_mels=64, t_out=None, layout='planar', peer_allreduce=False, **kwargs):
         self.wav, self.sample_rate, self.mode, self.n_mels, self.layout, self.kwargs = wav, sample_rate, mode, n_mels, layout, dict(kwargs)
         dev = wav.device
         n_clips = wav.shape[0]
@@ -283,6 +326,8 @@ class DatasetStep:
         self.mean = torch.empty(1, n_mels, self.n_ch, dtype=torch.float32, device=dev)
         self.std = torch.empty_like(self.mean)
         self.graph = None
+        # the statistics all-reduce: NCCL, or this package's one-launch exchange over peer memory
+        self.peer = PeerStatisticsAllReduce(self.acc.numel(), dev) if peer_allreduce else None
 
     def run(self, events=None):
         """Enqueue one step on the current stream.  events: optional 4 CUDA events recorded around the three stages."""
@@ -291,7 +336,7 @@ class DatasetStep:
         if events: events[1].record()
         self.acc.zero_()
         partial_statistics(self.feat, self.key, self.t_raw, self.acc, workspace=self.ws)
-        allreduce_statistics(self.acc)
+        allreduce_statistics(self.acc, self.peer)
         finish_statistics(self.acc, self.n_mels, self.n_ch, self.mean, self.std)
         if events: events[2].record()
         finalize_(self.feat, self.key, self.t_raw, self.mean, self.std)

@@ -100,3 +100,40 @@ def test_full_pipeline_matches_reference_main():
     assert got.shape == (4, 120, 64, 7)
     assert np.abs(got[..., :4] - want[..., :4]).max() <= 1e-4 / s64[..., :4].min() + 1e-4
     assert np.abs(got[..., 4:] - want[..., 4:]).max() <= 1e-3 / s64[..., 4:].min() + 1e-4
+
+
+def test_peer_allreduce_kernel_single_rank_and_repeated_epochs():
+    """seld_stats_peer_allreduce with one rank (its own buffer is the only peer): publish -> flag -> wait -> rank-ordered sum must
+    return the input unchanged, epoch after epoch (two alternating slots), also when replayed inside a CUDA graph.  The real
+    multi-GPU exchange is checked by bench.py's stats_check at N > 1 against single-GPU statistics."""
+    import torch
+    from seld_b200 import pipeline
+    n = 2 * 64 * 10 + 1
+    red = pipeline.PeerStatisticsAllReduce(n)
+    for it in range(5):
+        acc = torch.arange(n, dtype=torch.float64, device='cuda') * (it + 1) + 0.25
+        want = acc.clone()
+        red(acc)
+        assert torch.equal(acc, want)
+    acc = torch.full((n,), 3.5, dtype=torch.float64, device='cuda')
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        red(acc)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        red(acc)
+    for _ in range(4):
+        g.replay()
+    torch.cuda.synchronize()
+    assert bool((acc == 3.5).all())
+    # DatasetStep with the peer exchange == the plain step
+    from seld_b200.synth import make_clips
+    wav = make_clips(range(5), 480 * 60).cuda()
+    a = pipeline.DatasetStep(wav, 24000, mode='foa', t_out=50, win_length=960, hop_length=480, n_fft=1024)
+    b = pipeline.DatasetStep(wav, 24000, mode='foa', t_out=50, peer_allreduce=True, win_length=960, hop_length=480, n_fft=1024)
+    fa, ma, sa = a.run()
+    fb, mb, sb = b.run()
+    assert torch.equal(fa, fb) and torch.equal(ma, mb) and torch.equal(sa, sb)
