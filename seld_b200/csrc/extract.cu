@@ -141,9 +141,14 @@ struct SmemPlan {
 
 // Warps per CTA.  n_fft = 1024: up to 16 warps = 8 teams at 128 registers per thread (four warps per scheduler; measured
 // 2 -> 4 -> 8 warps with whole frames per warp: 35 -> 17.7 -> 11.5 ms, then teams of two: 12 warps 9.9 ms).
-// (MIC keeps 12: its bin phase is register-hungrier and measured 1.5 % slower at 128 registers.)
+// (Round 1's MIC kernel kept 12 warps at 168 registers: 18.0 ms at 16 against 17.0.  The fused-GCC kernel of round 2 is latency /
+//  issue bound with the phasor copy-out gone, fits 128 registers with 76 B of spills once the whole-frame register prefetch is
+//  dropped, and gains from the fourth warp per scheduler: 15.2 ms at 16 warps against 16.8 at 12, SELD_MIC_WARPS.)
 template <int R, int MODE>
-__host__ __device__ constexpr int max_warps() { return R <= 16 ? 16 : (R == 32 ? (MODE == MODE_FOA ? 16 : 12) : 4); }
+#ifndef SELD_MIC_WARPS
+#define SELD_MIC_WARPS 16
+#endif
+__host__ __device__ constexpr int max_warps() { return R <= 16 ? 16 : (R == 32 ? (MODE == MODE_FOA ? 16 : SELD_MIC_WARPS) : 4); }
 
 __device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
 __device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory"); }
@@ -289,7 +294,6 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     const long long total_frames = (long long)a.n_clips * a.frames_per_clip;
 
     float run_max = -INFINITY;
-    bool run_nan = false;
     int run_clip = -1;
     // fused GCC: partner team of the pair, its staged row, phase parities of the two teams' MMA barriers
     const int pteam = team ^ 1;
@@ -322,19 +326,18 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         }
     };
 
-    // running clip maximum of this warp; a NaN log-mel value makes it NaN (reference: db.max(), feature_extractor.py:65-71)
+    // running clip maximum of this warp; a NaN log-mel value makes it NaN (reference: db.max(), feature_extractor.py:65-71):
+    // every maximum on the way is NaN-propagating, the key of a NaN maximum sorts above +inf
+    auto max_key = [&](float m) -> unsigned { return (m != m) ? kNanKey : float_to_key(m); };
     auto note_max = [&](int clip, float mx) {
-        const bool nan_any = __any_sync(0xffffffffu, mx != mx);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        for (int o = 16; o > 0; o >>= 1) mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if (clip != run_clip) {
-            if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], run_nan ? kNanKey : float_to_key(run_max));
+            if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], max_key(run_max));
             run_clip = clip;
             run_max = -INFINITY;
-            run_nan = false;
         }
-        run_max = fmaxf(run_max, mx);
-        run_nan = run_nan || nan_any;
+        run_max = max_nan(run_max, mx);
     };
 
     // everything after the team's two packed FFTs: mel pieces, gather, GCC, row store, running clip maximum.
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         // are issued at the top of the frame instead and the other warps cover their latency.  Measured alternatives: requesting
         // them after the bin phase spills 376 B (12.3 ms instead of 9.2); staging them through tensor memory four taps per
         // bin step (tcgen05.st, then four tcgen05.ld at the next frame) couples the load latency into the team barriers (10.5 ms)
-        constexpr bool PREFETCH = !(R == 32 && MODE == MODE_FOA);
+        constexpr bool PREFETCH = !(R == 32 && (MODE == MODE_FOA || SELD_MIC_WARPS > 12));      // (experiment: MIC at 16 warps has no registers for it either)
         long long g = frame_index(sc, fi, team);
         long long gpart = FUSED ? frame_index(sc, fi, pteam) : -1;
         if (PREFETCH && g >= 0) request(g);
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         // frame t).  The 16-warp kernel parks those 17 taps in its own tensor-memory columns and fetches only the 15 new
         // ones from global memory for the following frame: half the global-load wavefronts, half the L2 requests.
         constexpr int SH = 15;
-        constexpr bool KEEP = !PREFETCH && TM && R == 32;
+        constexpr bool KEEP = !PREFETCH && TM && R == 32 && MODE == MODE_FOA;      // (the fused MIC kernel's tensor memory is full: tables + basis + accumulators)
         const bool keep_ok = KEEP && a.hop == SH * 32;
         const unsigned tkeep = taddr + TMEM_COL_KEEP + 64 * (warp >> 2);
         int prev_clip = -1, prev_t = -2;
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
             gpart = gpart_next;
         }
     }
-    if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], run_nan ? kNanKey : float_to_key(run_max));
+    if (run_clip >= 0 && lane == 0) atomicMax(&a.clip_max_key[run_clip], max_key(run_max));
     if constexpr (TM) {
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();

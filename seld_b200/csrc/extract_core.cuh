@@ -574,16 +574,21 @@ SELD_HD float fast_db(float x) {            // 10 log10(x), x > 0
 #endif
 }
 
-// 10 log10(max(power, 1e-10)) with torch.clamp's NaN behaviour (a NaN power stays NaN: reference :65-71 through amplitude_to_DB)
-SELD_HD float power_to_db(float pw) {
-    const float v = fast_db(fmaxf(pw, 1e-10f));
-    return (pw != pw) ? pw : v;
+// maximum that PROPAGATES NaN (torch.max / torch.clamp semantics; fmaxf would drop it): one FMNMX.NAN on the device
+SELD_HD float max_nan(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+#else
+    return (a != a || b != b) ? NAN : fmaxf(a, b);
+#endif
 }
+// 10 log10(max(power, 1e-10)); a NaN power stays NaN (reference :65-71 through amplitude_to_DB's clamp)
+SELD_HD float power_to_db(float pw) { return fast_db(max_nan(pw, 1e-10f)); }
 // TF variant: tfio dbscale = 10 log10(x^2) with NO floor (reference data_loader.py:323): log(0) = -inf survives until the
 // top_db clamp against the clip maximum
 SELD_HD float magnitude_to_db(float m) { return 2.0f * fast_db(m); }
-// running maximum that a NaN sticks to (torch's max propagates NaN)
-SELD_HD float max_nan(float m, float v) { return (v != v || m != m) ? NAN : fmaxf(m, v); }
 
 // ---------------------------------------------------------------- gather: pieces -> mel rows
 // Team lane u owns filters m = u, u + TL, ...: mel[m][c] = sum_{pieces of seg m} P.x + sum_{pieces of seg m-1} P.y, in
