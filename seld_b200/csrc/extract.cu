@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     // fused GCC: partner team of the pair, its staged row, phase parities of the two teams' MMA barriers
     const int pteam = team ^ 1;
     float* acc_part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(acc) + (pteam - team) * team_stride);
-    unsigned par_mine = 0, par_part = 0;
+    unsigned par_pair = 0;
     const unsigned tmem_base = taddr - ((32u * (warp & 3)) << 16);
     volatile unsigned* dead_flags = reinterpret_cast<volatile unsigned*>(nyq + GT_NYQ_BYTES);     // [2]: bits (channel 2h, 2h + 1) of warp h
 
@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     auto finish_frame = [&](bool mine, bool part, int clip, int t, float* row, auto&& early) {
         float mx = -INFINITY;
         if constexpr (FUSED) {
+            const int pair = team >> 1;
             if (mine) {
                 team_bar(bar_id);                                        // both spectra are in the tile
                 const unsigned dead = kGccDead ? (dead_flags[0] | (dead_flags[1] << 2)) : 0u;
@@ -352,22 +353,26 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                 else bin_phase_gcc_fused<false>(tile, nyq, tb, X, u, taddr + TMEM_COL_W01, 0u);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the phasor rows -> visible to the tensor core
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                team_bar(bar_id);
-                if (elect_one()) gcc_issue_mma(smem_addr(tile), tmem_base, gcc_dcol(team, 0), smem_addr(&s_mbar[team]), h);
+            }
+            pair_bar(9 + pair);                                          // both teams' rows are in place (or absent)
+            // one MMA chain per pair: the even team issues if it has a frame, else the odd one
+            if (mine && (!(team & 1) || !part)) {
+                if (elect_one())
+                    gcc_issue_mma(smem_addr(tile) - unsigned(team & 1) * unsigned(team_stride), unsigned(team_stride), tmem_base, gcc_dcol(pair),
+                                  smem_addr(&s_mbar[pair]), h);
                 __syncwarp();
-                mx = gather_lanes<MODE>(X, tb, acc, a.n_mels, u);       // log-mel while the MMAs run
-                mbar_wait_parity(smem_addr(&s_mbar[team]), par_mine);
-                par_mine ^= 1u;
             }
-            if (part) {
-                mbar_wait_parity(smem_addr(&s_mbar[pteam]), par_part);
-                par_part ^= 1u;
-            }
+            if (mine) mx = gather_lanes<MODE>(X, tb, acc, a.n_mels, u);  // log-mel while the MMAs run
+            mbar_wait_parity(smem_addr(&s_mbar[pair]), par_pair);
+            par_pair ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (mine) gcc_epilogue(taddr, gcc_dcol(team, 0), warp & 3, lane, acc);
-            if (part) gcc_epilogue(taddr, gcc_dcol(pteam, 0), warp & 3, lane, acc_part);
+            {
+                float* mine_row = mine ? acc : nullptr;
+                float* part_row = part ? acc_part : nullptr;
+                gcc_epilogue(taddr, gcc_dcol(pair), warp & 3, lane, (team & 1) ? part_row : mine_row, (team & 1) ? mine_row : part_row);
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            pair_bar(9 + (team >> 1));                                   // both rows are complete; both accumulators are free
+            pair_bar(9 + pair);                                          // both rows are complete; the accumulator is free
             if (!mine) return;
         } else {
             team_bar(bar_id);                                            // both spectra are in place

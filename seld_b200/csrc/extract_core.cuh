@@ -694,21 +694,22 @@ SELD_HD float gather_lanes(const float2* P, const Tables& tb, float* acc, int n_
 //     operand in TMEM): M = 64 occupies lanes 0..15 of each 32-lane subpartition, so two "atoms" interleave -- lanes 0..15
 //     hold K in [0, 512), lanes 16..31 hold K in [512, 1024) -- and the 128 KB basis takes 256 columns (probed on B200:
 //     tools/microbench/probe_tmem_ts.cu; A and D of one MMA must sit on the same datapath lanes).
-//   * B operand = the frame's six pair-phasor rows (N = 8 with two unused rows), written by the bin phase IN PLACE over
+//   * B operand = the six pair-phasor rows of the frames of a team PAIR (N = 16: two 8-row groups with two unused rows each,
+//     one per team), written by the bin phase IN PLACE over
 //     the team's spectrum in the no-swizzle K-major core-matrix layout: bin k of row r is the 32-bit word (re, im fp16) at
 //         (k >> 2) * 144 + r * 16 + (k & 3) * 4
 //     (16-byte K units of 8 rows, padded from 128 to 144 bytes: bank = (k + 4 r) mod 32, so both the stage-2 stores --
 //     lane = k mod 32 -- and the bin phase -- lane u owns bins 9u .. 9u + 8 -- are conflict-free).  Before the bin phase the
 //     same words hold the packed spectra: rows 0..3 = Re/Im Z0[k], Re/Im Z0[N-k], rows 4..7 the same of Z1.
-//   * D = 8 fp32 columns per team in TMEM (lower atom + upper atom, summed with one shuffle in the epilogue).
-// One elected thread issues 64 MMAs (M64 N8 K16, 8 cycles each, measured) per frame; nothing of this touches HBM.
+//   * D = 16 fp32 columns per team pair in TMEM (lower atom + upper atom, summed with one shuffle in the epilogue).
+// 64 MMAs (M64 N16 K16) per pair of frames; nothing of this touches HBM.
 #if defined(__CUDACC__)
 constexpr int GT_UNIT = 144;                    // byte pitch of a 16-byte K unit (8 rows)
 constexpr int GT_CHUNK = 8 * GT_UNIT;           // 32 bins
 constexpr int GT_BYTES = 128 * GT_UNIT;         // 512 bins: 18 432 bytes (the two exchange buffers alias its first 17 408)
 constexpr int GT_NYQ_BYTES = 128;               // Nyquist "column": rows 0, 1 = Z0[512], rows 4, 5 = Z1[512]
-constexpr int TMEM_COL_BASIS = 128, TMEM_COL_D = 384;         // D of team t: columns TMEM_COL_D + 8 t .. + 7
-__device__ __forceinline__ int gcc_dcol(int team, int) { return TMEM_COL_D + 8 * team; }
+constexpr int TMEM_COL_BASIS = 128, TMEM_COL_D = 384;         // D of team pair p: columns TMEM_COL_D + 16 p .. + 15 (even team's 8, odd team's 8)
+__device__ __forceinline__ int gcc_dcol(int pair) { return TMEM_COL_D + 16 * pair; }
 
 __device__ __forceinline__ bool elect_one() {   // one lane of a converged warp (lets ptxas issue UTCHMMA without a per-thread loop)
     unsigned pred;
@@ -859,17 +860,20 @@ __device__ __forceinline__ void mma_f16_ts(unsigned d_tmem, unsigned a_tmem, uns
                  :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// Issued by an elected thread of EACH warp of the team once the phasor rows are in place (and fenced to the async proxy):
-// warp h issues the 32 MMAs (K = 16 each) of atom h -- K half h of the basis, datapath lanes 16 h .. 16 h + 15 -- and
-// tcgen05.commit arrives on the team's mbarrier (count 2) when they have read the tile and written D.  (One thread issuing
-// all 64 held its warp ~600 cycles behind its partner at the next team barrier.)
-__device__ __forceinline__ void gcc_issue_mma(unsigned tile_saddr, unsigned tmem_base, int dcol, unsigned mbar_saddr, int half) {
+// Issued once per team PAIR and frame slot, after both teams' phasor rows are in place (and fenced to the async proxy): the two
+// tiles are the two 8-row groups of ONE N = 16 operand (SBO = byte distance between the teams' tiles), so a single chain of
+// MMAs (M64 N16 K16, ~11 cycles each -- measured, tools/microbench/probe_tmem_ts.cu -- against 2 x 8 for two N = 8 chains) serves
+// both frames: half the UTCHMMA instructions through the MIO queue.  An elected thread of each warp of the issuing team takes
+// atom h -- K half h of the basis, datapath lanes 16 h .. 16 h + 15 -- 32 MMAs, and tcgen05.commit arrives on the pair's
+// mbarrier (count 2) when they have read the tiles and written D.  A team without a frame contributes stale rows: its eight
+// accumulator columns are simply not read.
+__device__ __forceinline__ void gcc_issue_mma(unsigned tile0_saddr, unsigned tile_stride, unsigned tmem_base, int dcol, unsigned mbar_saddr, int half) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    constexpr unsigned idesc = (1u << 4) | ((8u >> 3) << 17) | ((64u >> 4) << 24);        // F32 accumulate, F16 x F16, K-major, N = 8, M = 64
+    constexpr unsigned idesc = (1u << 4) | ((16u >> 3) << 17) | ((64u >> 4) << 24);       // F32 accumulate, F16 x F16, K-major, N = 16, M = 64
     // no-swizzle K-major descriptor (cute::UMMA::SmemDescriptor): start address, LBO = 144 (K-adjacent core matrices),
-    // SBO (8-row groups; a single group here), version 1
-    const unsigned long long desc = (unsigned long long)((tile_saddr >> 4) & 0x3FFF) | ((unsigned long long)(GT_UNIT >> 4) << 16) |
-                                    ((unsigned long long)(GT_CHUNK >> 4) << 32) | (1ull << 46);
+    // SBO = distance between the two 8-row groups, version 1
+    const unsigned long long desc = (unsigned long long)((tile0_saddr >> 4) & 0x3FFF) | ((unsigned long long)(GT_UNIT >> 4) << 16) |
+                                    ((unsigned long long)((tile_stride >> 4) & 0x3FFF) << 32) | (1ull << 46);
     const unsigned up = unsigned(half) * (16u << 16);
     const unsigned d = tmem_base + dcol + up, a = tmem_base + TMEM_COL_BASIS + up;
     const unsigned long long desc_h = desc + (unsigned long long)(unsigned(half) * ((2 * GT_UNIT * 32) >> 4));
@@ -886,21 +890,25 @@ __device__ __forceinline__ void mbar_wait_parity(unsigned bar_saddr, unsigned pa
     } while (!done);
 }
 
-// Epilogue of one team's accumulator, executed by every warp of the team PAIR (four warps = the four TMEM subpartitions):
-// warp quadrant q holds lags 16 q .. 16 q + 15 -- K < 512 partial sums in lanes 0..15, K >= 512 in lanes 16..31.  The six
-// GCC channels of a lag are 24 contiguous bytes of the staged feature row.
-__device__ __forceinline__ void gcc_epilogue(unsigned taddr_quadrant, int dcol, int q, int lane, float* acc_row) {
-    float v[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "r"(taddr_quadrant + dcol) : "memory");
+// Epilogue of a pair's accumulator (16 columns: the even team's 8, the odd team's 8), executed by every warp of the pair (four
+// warps = the four TMEM subpartitions): warp quadrant q holds lags 16 q .. 16 q + 15 -- K < 512 partial sums in lanes 0..15,
+// K >= 512 in lanes 16..31.  The six GCC channels of a lag are 24 contiguous bytes of a team's staged feature row.
+__device__ __forceinline__ void gcc_epilogue(unsigned taddr_quadrant, int dcol, int q, int lane, float* acc_even, float* acc_odd) {
+    float v[16];
+    tmem_ld16(taddr_quadrant + dcol, v);
 #pragma unroll
-    for (int n = 0; n < 6; ++n) v[n] = (v[n] + __shfl_xor_sync(0xffffffffu, v[n], 16)) * (1.0f / 512.0f);     // the basis is stored x512
-    if (lane < 16) {
-        float2* d = reinterpret_cast<float2*>(acc_row + (16 * q + lane) * 10 + 4);
-        d[0] = make_float2(v[0], v[1]);
-        d[1] = make_float2(v[2], v[3]);
-        d[2] = make_float2(v[4], v[5]);
+    for (int t = 0; t < 2; ++t) {
+        float* acc_row = t ? acc_odd : acc_even;
+        if (acc_row == nullptr) continue;                                  // (warp-uniform: that team has no frame in this slot)
+        float w[6];
+#pragma unroll
+        for (int n = 0; n < 6; ++n) w[n] = (v[8 * t + n] + __shfl_xor_sync(0xffffffffu, v[8 * t + n], 16)) * (1.0f / 512.0f);     // the basis is stored x512
+        if (lane < 16) {
+            float2* d = reinterpret_cast<float2*>(acc_row + (16 * q + lane) * 10 + 4);
+            d[0] = make_float2(w[0], w[1]);
+            d[1] = make_float2(w[2], w[3]);
+            d[2] = make_float2(w[4], w[5]);
+        }
     }
 }
 #endif
