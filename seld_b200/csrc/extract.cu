@@ -78,6 +78,11 @@ struct ExtractArgs {
     int gcc_tc;               // MIC, n_fft 1024, 64 lags: fused tensor-core lag projection (extract_core.cuh)
     const void* gcc_basis;    // fp16 [64 lags][1024] basis of that projection (x512), row-major
     int tf_variant;           // FOA plan created with SELD_MODE_FOA_TF (magnitude mel, 20 log10, zero-padded tail)
+    int lanes;                // FOA, n_fft 1024: the bank has a flush-free lane form (mel_pieces.h)
+    const float* w4;          // [64 * 9][4] lane-form weights
+    const int* lane_beg;      // [64]
+    const int* gtab;          // [64][kLaneGatherMax]
+    int gather_n0, gather_n1;
     int frames_per_clip;      // frames this launch handles per clip (interior or edge count)
     int origin;               // frame t starts at sample t*hop - n_fft/2 + origin (0: centred STFT; n_fft/2: uncentred chunks)
     int fpw;                  // consecutive frames per team per super-chunk
@@ -102,6 +107,15 @@ __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 // Measured, 600 clips: 10.37 ms with it, 9.25 ms without -- 30 more live registers at the 128-register budget of four
 // warps per scheduler cost more (112 B of spills, a tighter gather) than the exposed load.
 constexpr bool kEarlyTail = SELD_EARLY_TAIL;
+#ifndef SELD_BULK_TAIL
+#define SELD_BULK_TAIL 1
+#endif
+// FOA, planar input: the 15 new taps of the team's NEXT frame (two channels x 1 920 contiguous bytes per warp) are staged through
+// shared memory by two cp.async.bulk copies issued right after the bin phase -- into the warp's own exchange buffer, which is dead
+// from there until the next frame's stage-1 store -- and read back with 30 conflict-free LDS at the top of the frame: no
+// registers are held across the gather (the early register request above lost to exactly that) and the HBM / L2 latency is off
+// the critical path.  north_star (1)'s "staged through TMA / shared memory", measured: see DESIGN.md 4.1.
+constexpr bool kBulkTail = SELD_BULK_TAIL;
 #ifndef SELD_GCC_DEAD
 #define SELD_GCC_DEAD 1
 #endif
@@ -112,11 +126,13 @@ constexpr int kGccNyqBytes = GT_NYQ_BYTES + 16;  // ... + the Nyquist column + t
 // Shared-memory plan of one kernel variant.  CTA-shared tables first, then one region per frame team (two warps): an
 // exchange buffer per warp (its spectrum overwrites it in place), the piece / GCC exchange buffer, the staged output row.
 // n_fft = 1024 keeps the per-lane constant tables in tensor memory, so only the small index tables stay here.
-template <int R, int MODE, bool TC>
+// TC: variant bits -- bit 0: MIC: fused tensor-core GCC / FOA: the TensorFlow variant; bit 1 (FOA, n_fft 1024): flush-free lane form of the mel bank
+template <int R, int MODE, int TC>
 struct SmemPlan {
     using G = Geo<R>;
     static constexpr bool TM = (R == 32);                               // per-lane constants in tensor memory
-    static constexpr bool tc = TC && MODE == MODE_MIC && R == 32;       // fused tensor-core GCC: the spectrum buffer doubles as the MMA's B tile
+    static constexpr bool tc = (TC & 1) && MODE == MODE_MIC && R == 32;       // fused tensor-core GCC: the spectrum buffer doubles as the MMA's B tile
+    static constexpr bool lanes = (TC & 2) && MODE == MODE_FOA && R == 32;    // flush-free lane form: two more index tables
     static constexpr bool NEED_TW = !TM || (MODE == MODE_MIC && !tc);   // stage-1 twiddles (also the fast CUDA-core GCC stage 2)
     static constexpr bool NEED_W01 = !TM;
     static constexpr bool NEED_WIN = !TM;
@@ -124,11 +140,14 @@ struct SmemPlan {
     __host__ __device__ static constexpr int table_bytes(int n_mels) {
         return (NEED_TW ? align16(G::N * 8) : 0) + (NEED_W01 ? align16(G::TL * G::BPT * 8) : 0) + align16(G::TL * 8) + 2 * align16(G::TL * 4) +
                align16((n_mels + 2) * 4) + align16(64 * 4) + 16 + (NEED_WIN ? align16(G::N * 4) : 0) + (NEED_TWLIN ? align16(G::N * 8) : 0) +
-               (tc ? 64 : 0);                                           // one mbarrier per frame team
+               (tc ? 64 : 0) +                                          // one mbarrier per frame team
+               ((kBulkTail && MODE == MODE_FOA && R == 32) ? 128 : 0) +  // one mbarrier per warp (bulk-staged tail taps)
+               (lanes ? align16(G::TL * 4) + align16(64 * kLaneGatherMax * 4) : 0);
     }
     __host__ __device__ static constexpr int x_bytes(int n_slots) {
         const int pieces = align16(n_slots * PieceGeo<MODE>::PSTRIDE * 8);
         const int exchange = (MODE == MODE_MIC && !tc) ? align16(G::E_ELEMS * 8) : 0;
+        if (lanes) return align16((kLaneZeroRec + 1) * kLaneRecWords * 4);      // 64 lane records + the zero record
         return pieces > exchange ? pieces : exchange;
     }
     __host__ __device__ static constexpr int spec_bytes() {            // the two exchange / spectrum buffers of a team
@@ -159,7 +178,7 @@ __device__ __forceinline__ unsigned smem_addr(const void* p) { return static_cas
 // TC (MIC, n_fft 1024, 64 lags): the GCC lag projection runs on the tensor cores inside this kernel (extract_core.cuh,
 // "fused tensor-core GCC").  Two neighbouring teams form a PAIR there: their four warps cover the four tensor-memory
 // subpartitions, which is what reading an M = 64 accumulator back takes, so the pair reads both teams' accumulators.
-template <int R, int MODE, int LAYOUT, bool EDGE, bool TC>
+template <int R, int MODE, int LAYOUT, bool EDGE, int TC>
 __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(ExtractArgs a) {
     using G = Geo<R>;
     constexpr int C = (MODE == MODE_FOA) ? 7 : 10;
@@ -178,7 +197,8 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     constexpr bool FUSED = SP::tc;
     // TC on a FOA plan selects the TensorFlow variant of the features (reference data_loader.py:310-349,
     // get_preprocessed_x_tf): mel bank on |X|, 20 log10 without a floor, frames from sample 0 with a zero-padded tail
-    constexpr bool TFV = TC && MODE == MODE_FOA;
+    constexpr bool TFV = (TC & 1) && MODE == MODE_FOA;
+    constexpr bool LANES = SP::lanes;
     // ---- CTA-shared tables
     unsigned char* p = smem;
     float2* s_tw_t = nullptr;
@@ -197,6 +217,17 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     if constexpr (SP::NEED_TWLIN) { s_tw_lin = reinterpret_cast<float2*>(p);  p += align16(G::N * 8); }
     unsigned long long* s_mbar = nullptr;                                    // fused GCC: "the MMAs of team t have completed"
     if constexpr (FUSED) { s_mbar = reinterpret_cast<unsigned long long*>(p);  p += 64; }
+    int* s_lane_beg = nullptr;
+    int* s_gtab = nullptr;
+    if constexpr (LANES) {
+        s_lane_beg = reinterpret_cast<int*>(p);  p += align16(TL * 4);
+        s_gtab = reinterpret_cast<int*>(p);  p += align16(64 * kLaneGatherMax * 4);
+        for (int i = threadIdx.x; i < TL; i += blockDim.x) s_lane_beg[i] = a.lane_beg[i];
+        for (int i = threadIdx.x; i < 64 * kLaneGatherMax; i += blockDim.x) s_gtab[i] = a.gtab[i];
+    }
+    constexpr bool BULK = kBulkTail && MODE == MODE_FOA && R == 32 && !EDGE && LAYOUT == LAYOUT_PLANAR_CL;
+    unsigned long long* s_ldbar = nullptr;                                   // bulk-staged tail taps: one mbarrier per warp
+    if constexpr (kBulkTail && MODE == MODE_FOA && R == 32) { s_ldbar = reinterpret_cast<unsigned long long*>(p);  p += 128; }
     const float wscale = ((EDGE ? a.layout : LAYOUT) == LAYOUT_PCM16_LC) ? (1.0f / 32768.0f) : 1.0f;    // exact: folds the PCM decode
     for (int i = threadIdx.x; i < G::N; i += blockDim.x) {
         if constexpr (SP::NEED_WIN) s_win[i] = a.window[i] * wscale;
@@ -210,6 +241,12 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         s_slot0[threadIdx.x] = a.slot0[threadIdx.x];
         s_slot1[threadIdx.x] = a.slot1[threadIdx.x];
         s_ov[threadIdx.x] = a.ov[threadIdx.x];
+    }
+    if constexpr (BULK) {
+        if (threadIdx.x < 16) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&s_ldbar[threadIdx.x])));
+            asm volatile("fence.mbarrier_init.release.cluster;");
+        }
     }
     if constexpr (FUSED) {
         if (threadIdx.x < 8) {
@@ -243,12 +280,24 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                 for (int i = 0; i < 8; ++i) { const float2 t = a.tw_t[(8 * g + i) * 32 + lane]; r[2 * i] = t.x; r[2 * i + 1] = t.y; }
                 tmem_st16(taddr + TMEM_COL_TW + 16 * g, r);
             }
-            const float* w01 = reinterpret_cast<const float*>(a.w01) + size_t(u) * (2 * G::BPT);     // u: quadrant parity == warp parity
+            if constexpr (LANES) {                // 4 weights per bin step: columns 96 .. 131
+                const float* w4 = a.w4 + size_t(u) * (4 * G::BPT);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < 2; ++c) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = (16 * c + i < 2 * G::BPT) ? w01[16 * c + i] : 0.f;
-                tmem_st16(taddr + TMEM_COL_W01 + 16 * c, r);
+                    for (int i = 0; i < 16; ++i) r[i] = w4[16 * c + i];
+                    tmem_st16(taddr + TMEM_COL_W01 + 16 * c, r);
+                }
+                tmem_st2(taddr + TMEM_COL_W01 + 32, w4[32], w4[33]);
+                tmem_st2(taddr + TMEM_COL_W01 + 34, w4[34], w4[35]);
+            } else {
+                const float* w01 = reinterpret_cast<const float*>(a.w01) + size_t(u) * (2 * G::BPT);     // u: quadrant parity == warp parity
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = (16 * c + i < 2 * G::BPT) ? w01[16 * c + i] : 0.f;
+                    tmem_st16(taddr + TMEM_COL_W01 + 16 * c, r);
+                }
             }
             if constexpr (FUSED) {
                 // the lag-projection basis, A operand of every MMA of this kernel: lane l of quadrant q holds lag row
@@ -290,7 +339,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     if constexpr (TM) asm volatile("tcgen05.fence::after_thread_sync;");
     const float* wlane = SP::NEED_WIN ? s_win + lane : nullptr;      // window taps of this lane when they are not in TMEM
 
-    const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_slot0, s_slot1, s_pb, s_ov};
+    const Tables tb{nullptr, s_tw_t, s_tw_lin, s_w01, s_endmask, s_slot0, s_slot1, s_pb, s_ov, nullptr, s_lane_beg, s_gtab, a.gather_n0, a.gather_n1};
     const long long total_frames = (long long)a.n_clips * a.frames_per_clip;
 
     float run_max = -INFINITY;
@@ -376,10 +425,12 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
             if (!mine) return;
         } else {
             team_bar(bar_id);                                            // both spectra are in place
-            bin_phase<R, MODE, TM, TFV>(S0, S1, tb, X, 1e-8f, u, taddr + TMEM_COL_W01);
+            if constexpr (LANES) bin_phase_lanes<R, TM, TFV>(S0, S1, tb, X, 1e-8f, u, taddr + TMEM_COL_W01);
+            else bin_phase<R, MODE, TM, TFV>(S0, S1, tb, X, 1e-8f, u, taddr + TMEM_COL_W01);
             team_bar(bar_id);
             early();                                                     // (FOA: the next frame's new samples are requested here)
-            mx = a.seg_major ? gather_lanes<MODE, TFV>(X, tb, acc, a.n_mels, u) : gather_phase<MODE, TFV>(X, tb, acc, a.n_mels, u);
+            if constexpr (LANES) mx = gather_records<TFV>(X, tb, acc, a.n_mels, u);
+            else mx = a.seg_major ? gather_lanes<MODE, TFV>(X, tb, acc, a.n_mels, u) : gather_phase<MODE, TFV>(X, tb, acc, a.n_mels, u);
             if constexpr (MODE == MODE_MIC) {
                 team_bar(bar_id);                                        // pieces consumed: X is the GCC exchange buffer now
                 if (h == 0) {
@@ -509,7 +560,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         constexpr int SH = 15;
         constexpr bool KEEP = !PREFETCH && TM && R == 32 && MODE == MODE_FOA;      // (the fused MIC kernel's tensor memory is full: tables + basis + accumulators)
         const bool keep_ok = KEEP && a.hop == SH * 32;
-        const unsigned tkeep = taddr + TMEM_COL_KEEP + 64 * (warp >> 2);
+        const unsigned tkeep = taddr + TMEM_COL_KEEP + (LANES ? 8 : 0) + 64 * (warp >> 2);      // (the lane form's weights end at column 132)
         int prev_clip = -1, prev_t = -2;
         // taps [n_lo, n_hi) of the frame starting at sample `fs` of clip `c` (this warp's channel pair) -> r[]
         auto load_taps = [&](int c, long long fs, int n_lo, int n_hi, float2* r) {
@@ -530,6 +581,8 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         };
         // (kEarlyTail: the SH new taps of the team's NEXT frame requested right after the bin phase)
         bool have_tail = false;                       // every frame but a warp's first gets its tail early
+        unsigned ld_parity = 0;
+        const bool bulk_ok = BULK && a.hop % 4 == 0 && a.n_samples % 4 == 0 && a.origin % 4 == 0;      // 16-byte aligned bulk copies
         // (prefetching just the 15 new taps of the next frame in 30 registers was tried on top of this: 104 B of spills and
         //  9.58 ms instead of 9.06)
         // (Fused GCC: deferring a frame's epilogue into the next iteration -- accumulators and staged rows double-buffered, the
@@ -563,7 +616,16 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                     } else {
                         load_taps(clip, start, 0, R - SH, raw);
                     }
-                    if (!(kEarlyTail && have_tail)) load_taps(clip, start, R - SH, R, raw);   // (else requested before the previous gather)
+                    if (BULK && bulk_ok && have_tail) {       // staged by the bulk copies issued after the previous bin phase
+                        mbar_wait_parity(smem_addr(&s_ldbar[warp]), ld_parity);
+                        ld_parity ^= 1u;
+                        const float* ea = reinterpret_cast<const float*>(E) + lane;
+#pragma unroll
+                        for (int n2 = R - SH; n2 < R; ++n2) raw[n2] = make_float2(ea[32 * (n2 - (R - SH))], ea[32 * SH + 32 * (n2 - (R - SH))]);
+                        __syncwarp();                         // every lane has its taps before anyone's stage-1 store lands in E
+                    } else if (!(kEarlyTail && have_tail)) {
+                        load_taps(clip, start, R - SH, R, raw);   // (kEarlyTail: requested before the previous gather)
+                    }
                     have_tail = true;
                     if (keep_ok) {                                                // taps 15 .. 31 are taps 0 .. 16 of the next frame
                         const float* rf = reinterpret_cast<const float*>(raw);
@@ -598,7 +660,21 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                 __syncwarp();
                 stage2();
                 finish_frame(true, gpart >= 0, clip_now, t_now, row, [&] {
-                    if constexpr (KEEP && kEarlyTail) {
+                    if constexpr (BULK) {
+                        if (bulk_ok && g_next >= 0 && lane == 0) {
+                            const int c2 = int(g_next / a.frames_per_clip);
+                            const int t2 = a.t_lo + int(g_next - (long long)c2 * a.frames_per_clip);
+                            const long long s2 = (long long)t2 * a.hop - G::N / 2 + a.origin + 32 * (R - SH);
+                            const float* pa = a.wav + ((long long)c2 * 4 + 2 * h) * a.n_samples + s2;
+                            const unsigned bar = smem_addr(&s_ldbar[warp]), dst = smem_addr(E);
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // E was read through the generic proxy
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2 * 32 * SH * 4) : "memory");
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         :: "r"(dst), "l"(pa), "r"(32 * SH * 4), "r"(bar) : "memory");
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         :: "r"(dst + 32 * SH * 4), "l"(pa + a.n_samples), "r"(32 * SH * 4), "r"(bar) : "memory");
+                        }
+                    } else if constexpr (KEEP && kEarlyTail) {
                         if (g_next >= 0) {
                             const int c2 = int(g_next / a.frames_per_clip);
                             const int t2 = a.t_lo + int(g_next - (long long)c2 * a.frames_per_clip);
@@ -624,7 +700,7 @@ __global__ void clip_max_decode_kernel(const unsigned int* keys, int n, float* o
     if (i < n) out[i] = key_to_float(keys[i]);
 }
 
-template <int R, int MODE, int LAYOUT, bool EDGE, bool TC>
+template <int R, int MODE, int LAYOUT, bool EDGE, int TC>
 static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream) {
     a.frames_per_clip = EDGE ? a.t_lo + (a.t_tot - a.t_hi) : a.t_hi - a.t_lo;
     if (a.frames_per_clip <= 0) return SELD_OK;
@@ -659,12 +735,12 @@ static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream)
     return SELD_OK;
 }
 
-template <int R, int MODE, bool TC>
+template <int R, int MODE, int TC>
 static int launch_kernels(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
     int rc;
     if (a.layout == LAYOUT_PLANAR_CL) rc = launch_one<R, MODE, LAYOUT_PLANAR_CL, false, TC>(plan, a, stream);
     else if (a.layout == LAYOUT_INTERLEAVED_LC) rc = launch_one<R, MODE, LAYOUT_INTERLEAVED_LC, false, TC>(plan, a, stream);
-    else if constexpr (MODE == MODE_FOA && TC) { set_error("the TF-variant extractor takes float32 input"); return SELD_EUNSUPPORTED; }
+    else if constexpr (MODE == MODE_FOA && (TC & 1)) { set_error("the TF-variant extractor takes float32 input"); return SELD_EUNSUPPORTED; }
     else rc = launch_one<R, MODE, LAYOUT_PCM16_LC, false, TC>(plan, a, stream);
     if (rc != SELD_OK) return rc;
     return launch_one<R, MODE, LAYOUT_PLANAR_CL, true, TC>(plan, a, stream);  // edge frames: layout taken from a.layout
@@ -673,11 +749,12 @@ static int launch_kernels(const seld_plan* plan, const ExtractArgs& a, cudaStrea
 template <int R, int MODE>
 static int launch_mode(const seld_plan* plan, const ExtractArgs& a, cudaStream_t stream) {
     constexpr bool can_tc = (MODE == MODE_MIC && R == 32);
-    if (can_tc && a.gcc_tc) return launch_kernels<R, MODE, can_tc>(plan, a, stream);
+    if (can_tc && a.gcc_tc) return launch_kernels<R, MODE, can_tc ? 1 : 0>(plan, a, stream);
     if constexpr (MODE == MODE_FOA && R == 32) {
-        if (a.tf_variant) return launch_kernels<R, MODE, true>(plan, a, stream);
+        if (a.lanes) return a.tf_variant ? launch_kernels<R, MODE, 3>(plan, a, stream) : launch_kernels<R, MODE, 2>(plan, a, stream);
+        if (a.tf_variant) return launch_kernels<R, MODE, 1>(plan, a, stream);
     }
-    return launch_kernels<R, MODE, false>(plan, a, stream);
+    return launch_kernels<R, MODE, 0>(plan, a, stream);
 }
 
 template <int R>
@@ -796,6 +873,12 @@ int seld_plan_create(int sample_rate, int n_fft, int win_length, int hop_length,
     up((void**)&plan->slot1, mp.slot1.data(), sizeof(int) * mp.slot1.size());
     up((void**)&plan->ov, mp.ov.data(), sizeof(int) * mp.ov.size());
     up((void**)&plan->pb, mp.pb.data(), sizeof(int) * mp.pb.size());
+    plan->lanes_ok = mp.lanes_ok ? 1 : 0;
+    plan->gather_n[0] = mp.gather_n[0];
+    plan->gather_n[1] = mp.gather_n[1];
+    up((void**)&plan->w4, mp.w4.data(), sizeof(float) * mp.w4.size());
+    up((void**)&plan->lane_beg, mp.lane_beg.data(), sizeof(int) * mp.lane_beg.size());
+    up((void**)&plan->gtab, mp.gtab.data(), sizeof(int) * mp.gtab.size());
     if (e != cudaSuccess) {
         seld_plan_destroy(plan);
         return cuda_fail(e, "plan table upload");
@@ -852,6 +935,9 @@ int seld_plan_destroy(seld_plan_t plan) {
     cudaFree(plan->slot1);
     cudaFree(plan->ov);
     cudaFree(plan->pb);
+    cudaFree(plan->w4);
+    cudaFree(plan->lane_beg);
+    cudaFree(plan->gtab);
     cudaFree(plan->gcc_bt);
     delete plan;
     return SELD_OK;
@@ -910,6 +996,13 @@ static int extract_common(seld_plan_t plan, const void* wav_void, int layout, in
     a.gcc_basis = plan->gcc_bt;
     a.seg_major = plan->seg_major;
     a.x_zero_f2 = plan->seg_major ? plan->n_slots * (plan->mode == SELD_MODE_FOA ? PieceGeo<MODE_FOA>::PSTRIDE : PieceGeo<MODE_MIC>::PSTRIDE) : 0;
+    a.lanes = (plan->lanes_ok && plan->mode == SELD_MODE_FOA && plan->n_fft == 1024 && !getenv("SELD_NO_LANES")) ? 1 : 0;
+    a.w4 = plan->w4;
+    a.lane_beg = plan->lane_beg;
+    a.gtab = plan->gtab;
+    a.gather_n0 = plan->gather_n[0];
+    a.gather_n1 = plan->gather_n[1];
+    if (a.lanes) a.x_zero_f2 = (kLaneZeroRec + 1) * (kLaneRecWords / 2);      // (only the never-written zero record matters)
     // frames [t_lo, t_hi) need no reflection: t*hop - n_fft/2 >= 0 and t*hop + n_fft/2 <= n_samples
     {
         const long long half = plan->n_fft / 2;

@@ -49,6 +49,11 @@ struct Tables {             // CTA-shared constant tables (shared memory on the 
     const int* slot1;           // [TL]     slot of its second piece (later pieces follow at +1); layouts: mel_pieces.h
     const int* pb;              // [n_mels + 2] compact layout: pieces with seg == m are [pb[m+1], pb[m+2])
     const int* ov;              // [64] segment-major layout: overflow slots of the 3rd / 4th piece of a segment
+    // flush-free lane form of the bank (mel_pieces.h; null / 0 where it does not apply)
+    const float* w4;            // [TL*BPT][4] per-bin weights into the lane's four filters (device: tensor memory instead)
+    const int* lane_beg;        // [TL] first bin of lane u
+    const int* gtab;            // [64][kLaneGatherMax] record words of filter m
+    int gather_n0, gather_n1;   // table entries the filters of team warp 0 / 1 need
 };
 
 struct ClipSrc {            // one clip's samples: channel c, sample i -> base[c * chan_stride + i * samp_stride]
@@ -291,6 +296,10 @@ constexpr int TMEM_COL_WIN = 0, TMEM_COL_TW = 32, TMEM_COL_W01 = 96, TMEM_COL_KE
 __device__ __forceinline__ void tmem_ld2(unsigned taddr, float& a, float& b) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\ttcgen05.wait::ld.sync.aligned;"
                  : "=f"(a), "=f"(b) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(unsigned taddr, float& a, float& b, float& c, float& d) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(unsigned taddr, float* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
@@ -566,6 +575,69 @@ SELD_HD void bin_phase(float2* S0, float2* S1, const Tables& tb, float2* P, floa
     }
 }
 
+// ---------------------------------------------------------------- bin phase, flush-free lane form (FOA)
+// Same per-bin arithmetic as bin_phase<MODE_FOA>; the mel projection differs: lane u's run of bins touches at most four
+// consecutive filters (mel_pieces.h), which it accumulates as two packed pairs A = (F0, F1), B = (F2, F3) per channel with the
+// per-bin weights (a0, a1, b0, b1) -- two FFMA2 per channel and bin, NO per-bin flush (the piece form spends 7 FMUL2 + 7
+// predicated 64-bit stores + slot bookkeeping on every bin although 113 of 576 slots end a piece) -- and stores one record of
+// 14 float2 at the end.  Fixed order, no atomics => bit-reproducible.
+template <int R, bool W_TMEM = false, bool MAG = false>
+SELD_HD void bin_phase_lanes(const float2* S0, const float2* S1, const Tables& tb, float2* P, float eps, int u, unsigned taddr_w4 = 0) {
+    using G = Geo<R>;
+    constexpr int N = G::N;
+    const int kbeg = tb.lane_beg[u];
+    float2 A[7], B[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) { A[c] = make_float2(0.f, 0.f); B[c] = make_float2(0.f, 0.f); }
+    const float inv_eps = 1.0f / eps;
+#pragma unroll
+    for (int i = 0; i < G::BPT; ++i) {
+        const int k = kbeg + i;                        // (bins past the lane's run, or past F - 1, carry zero weights)
+        const int kn = (N - k) & (N - 1);
+        const float2 z0 = S0[k], z0n = S0[kn], z1 = S1[k], z1n = S1[kn];
+        float2 ch[4];                                  // twice the channel spectra
+        ch[0] = make_float2(z0.x + z0n.x, z0.y - z0n.y);
+        ch[1] = make_float2(z0.y + z0n.y, z0n.x - z0.x);
+        ch[2] = make_float2(z1.x + z1n.x, z1.y - z1n.y);
+        ch[3] = make_float2(z1.y + z1n.y, z1n.x - z1.x);
+        float val[7];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) val[c] = fmaf(ch[c].x, ch[c].x, ch[c].y * ch[c].y);     // 4 |X_c|^2
+        if constexpr (MAG) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) val[c] = sqrt_ftz(4.0f * val[c]);                   // TF variant: 4 |X_c|
+        }
+        const float ix = fmaf(ch[0].x, ch[3].x, ch[0].y * ch[3].y);
+        const float iy = fmaf(ch[0].x, ch[1].x, ch[0].y * ch[1].y);
+        const float iz = fmaf(ch[0].x, ch[2].x, ch[0].y * ch[2].y);
+        const float inv4 = fminf(4.0f * rsqrt_ftz(fmaf(ix, ix, fmaf(iy, iy, iz * iz))), inv_eps);
+        val[4] = ix * inv4;
+        val[5] = iy * inv4;
+        val[6] = iz * inv4;
+        float2 wa, wb;
+#if defined(__CUDA_ARCH__)
+        if constexpr (W_TMEM) {
+            tmem_ld4(taddr_w4 + 4 * i, wa.x, wa.y, wb.x, wb.y);
+        } else {
+            const float* w = tb.w4 + (size_t(u) * G::BPT + i) * 4;
+            wa = make_float2(w[0], w[1]); wb = make_float2(w[2], w[3]);
+        }
+#else
+        (void)taddr_w4;
+        const float* w = tb.w4 + (size_t(u) * G::BPT + i) * 4;
+        wa = make_float2(w[0], w[1]); wb = make_float2(w[2], w[3]);
+#endif
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            A[c] = pfma(make_float2(val[c], val[c]), wa, A[c]);
+            B[c] = pfma(make_float2(val[c], val[c]), wb, B[c]);
+        }
+    }
+    float2* rec = P + u * (kLaneRecWords / 2);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) { rec[2 * c] = A[c]; rec[2 * c + 1] = B[c]; }
+}
+
 SELD_HD float fast_db(float x) {            // 10 log10(x), x > 0
 #if defined(__CUDA_ARCH__)
     return 3.0102999566398120f * __log2f(x);     // MUFU.LG2: <= 2 ulp of log2 => <= 2.3e-5 dB at -100 dB, ~6e-6 dB typical
@@ -676,6 +748,37 @@ SELD_HD float gather_lanes(const float2* P, const Tables& tb, float* acc, int n_
 #pragma unroll
         for (int c = 0; c < NV; ++c) {
             float v = A[c].x + below[c];
+            if (c < 4) {
+                v = MAG ? magnitude_to_db(v) : power_to_db(v);
+                mx = max_nan(mx, v);
+            }
+            acc[u * C + c] = v;
+        }
+    }
+    return mx;
+}
+
+// Gather of the lane form: filter m = team lane u adds the (at most gather_n) records gtab[m] names, in table order (absent
+// entries point at the never-written zero record).
+template <bool MAG = false>
+SELD_HD float gather_records(const float2* P, const Tables& tb, float* acc, int n_mels, int u) {
+    constexpr int C = 7;
+    const float* W = reinterpret_cast<const float*>(P);
+    const int* gt = tb.gtab + u * kLaneGatherMax;
+    const int n = (u < 32) ? tb.gather_n0 : tb.gather_n1;            // warp-uniform
+    float sum[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) sum[c] = 0.f;
+    for (int t = 0; t < n; ++t) {
+        const float* r = W + gt[t];
+#pragma unroll
+        for (int c = 0; c < C; ++c) sum[c] += r[4 * c];
+    }
+    float mx = -INFINITY;
+    if (u < n_mels) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float v = sum[c];
             if (c < 4) {
                 v = MAG ? magnitude_to_db(v) : power_to_db(v);
                 mx = max_nan(mx, v);

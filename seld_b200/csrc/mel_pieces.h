@@ -30,7 +30,22 @@ struct MelPieces {
     bool seg_major = false;
     int n_slots = 0;
     std::vector<int> ov;                          // [64]
+    // ---- flush-free "lane" form (FOA, n_fft 1024): lane u owns bins [lane_beg[u], lane_beg[u] + bpt) -- at most bpt of them count,
+    // cut so that a lane touches at most kLaneSegs consecutive segments, hence at most kLaneSegs + 1 = 4 consecutive filters
+    // seg0 .. seg0 + 3.  It accumulates those four partial sums per channel as two packed pairs with per-bin weights
+    // w4 = (a0, a1, b0, b1), no flush inside the bin loop, and stores ONE record; filter m then adds the few records gtab[m] names.
+    bool lanes_ok = false;
+    std::vector<int> lane_beg;                    // [64]
+    std::vector<int> lane_seg0;                   // [64]
+    std::vector<float> w4;                        // [64 * bpt][4]  0.25 * weights into filters seg0, seg0 + 1 | seg0 + 2, seg0 + 3
+    std::vector<int> gtab;                        // [64][kLaneGatherMax] word offset (lane * kLaneRecWords + j) of the t-th record of filter m
+    int gather_n[2] = {0, 0};                     // entries the filters of team warp 0 / 1 need at most
 };
+
+constexpr int kLaneSegs = 3;
+constexpr int kLaneRecWords = 30;                 // 7 channels x (F0, F1, F2, F3) = 28 words, padded to an even, bank-friendly pitch
+constexpr int kLaneGatherMax = 8;
+constexpr int kLaneZeroRec = 64;                  // record 64 is never written: absent table entries point at it
 
 constexpr int kSegMajorRanks = 4;
 constexpr int kSegMajorPitch = 65;      // odd, so the pieces of one segment land in different bank groups
@@ -126,6 +141,59 @@ inline std::string build_mel_pieces(const float* fb, int n_bins, int n_mels, Mel
         out.slot1[l] = piece_seg[p] + 1;                      // later pieces of the lane open their segment: rank 0
     }
     out.n_slots = out.seg_major ? 2 * kSegMajorPitch + n_over : out.n_pieces;
+
+    // ---- lane form: greedy cut of the bin axis into <= 64 runs of <= bpt bins over <= kLaneSegs consecutive segments
+    out.lanes_ok = false;
+    out.lane_beg.assign(TL, 0);
+    out.lane_seg0.assign(TL, 0);
+    out.w4.assign(size_t(TL) * bpt * 4, 0.f);
+    out.gtab.assign(size_t(64) * kLaneGatherMax, kLaneZeroRec * kLaneRecWords);
+    out.gather_n[0] = out.gather_n[1] = 0;
+    if (n_mels <= 64) {
+        bool ok = true;
+        int lane = 0, k = 0;
+        std::vector<std::vector<int>> users(n_mels);          // filter -> (lane * kLaneRecWords + j) of every record that feeds it
+        while (k < n_bins && ok) {
+            if (lane >= TL) { ok = false; break; }
+            const int beg = k;
+            int s0 = -1, s_last = -1, n = 0;
+            while (k < n_bins && n < bpt) {
+                const int sg = seg[k];
+                if (sg >= 0) {
+                    if (s0 < 0) s0 = sg;
+                    if (sg - s0 >= kLaneSegs) break;           // a fourth segment: the next lane takes it
+                    s_last = sg;
+                }
+                ++k; ++n;
+            }
+            out.lane_beg[lane] = beg;
+            out.lane_seg0[lane] = s0 < 0 ? 0 : s0;
+            bool feeds[4] = {false, false, false, false};
+            for (int i = 0; i < k - beg; ++i) {
+                const int kk = beg + i, sg = seg[kk];
+                if (sg < 0) continue;
+                const int r = sg - s0;                         // 0, 1, 2
+                const float w0 = out.w01[2 * size_t(kk)], w1 = out.w01[2 * size_t(kk) + 1];
+                float* w = &out.w4[(size_t(lane) * bpt + i) * 4];
+                if (r == 0) { w[0] = w0; w[1] = w1; }
+                else if (r == 1) { w[1] = w0; w[2] = w1; }
+                else { w[2] = w0; w[3] = w1; }
+                if (w0 != 0.f) feeds[r] = true;
+                if (w1 != 0.f) feeds[r + 1] = true;
+            }
+            for (int j = 0; j < 4; ++j)
+                if (feeds[j] && s0 + j < n_mels) users[s0 + j].push_back(lane * kLaneRecWords + j);
+            ++lane;
+        }
+        for (int m = 0; m < n_mels && ok; ++m) {
+            if (int(users[m].size()) > kLaneGatherMax) { ok = false; break; }
+            for (size_t t = 0; t < users[m].size(); ++t) out.gtab[size_t(m) * kLaneGatherMax + t] = users[m][t];
+            int& gn = out.gather_n[m < 32 ? 0 : 1];
+            if (int(users[m].size()) > gn) gn = int(users[m].size());
+        }
+        // lanes past the last run keep beg = 0 and zero weights: they read bins 0 .. bpt - 1 and contribute nothing
+        out.lanes_ok = ok && (n_bins + bpt <= 2 * (n_bins - 1));   // a lane's bpt reads stay inside the n_fft-long spectrum buffer
+    }
     return "";
 }
 

@@ -26,6 +26,11 @@ struct seld_plan {
     int* slot1;      // [64]
     int* ov;         // [64]  overflow slots of the segment-major record layout
     int* pb;         // [n_mels + 2]
+    float* w4;       // [64 * bins_per_lane][4]  flush-free lane form of the bank (mel_pieces.h)
+    int* lane_beg;   // [64]
+    int* gtab;       // [64][kLaneGatherMax]
+    int gather_n[2];
+    int lanes_ok;
     void* gcc_bt;    // MIC, n_fft 1024, 64 lags: fp16 [64][1024] basis of the tensor-core lag projection (else null)
     int n_pieces;
     int n_slots;     // piece records per frame in the layout in use

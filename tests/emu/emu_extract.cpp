@@ -45,10 +45,15 @@ static void run(const float* wav, int n_clips, long long L, int hop, int n_mels,
             stage2_inplace(EA);
             for (int l = 0; l < 32; ++l) stage1_forward<R, LAYOUT>(src, 2, 3, start, wreg[l], tb, EB.data(), l);
             stage2_inplace(EB);
-            for (int u = 0; u < G::TL; ++u) bin_phase<R, MODE>(EA.data(), EB.data(), tb, X.data(), 1e-8f, u);
-            for (int u = 0; u < G::TL; ++u)
-                cmax = fmaxf(cmax, fast_gather ? gather_lanes<MODE>(X.data(), tb, acc.data(), n_mels, u)
-                                               : gather_phase<MODE>(X.data(), tb, acc.data(), n_mels, u));
+            if (MODE == MODE_FOA && R == 32 && tb.w4) {                      // the flush-free lane form, as the device selects it
+                for (int u = 0; u < G::TL; ++u) bin_phase_lanes<R>(EA.data(), EB.data(), tb, X.data(), 1e-8f, u);
+                for (int u = 0; u < G::TL; ++u) cmax = fmaxf(cmax, gather_records<>(X.data(), tb, acc.data(), n_mels, u));
+            } else {
+                for (int u = 0; u < G::TL; ++u) bin_phase<R, MODE>(EA.data(), EB.data(), tb, X.data(), 1e-8f, u);
+                for (int u = 0; u < G::TL; ++u)
+                    cmax = fmaxf(cmax, fast_gather ? gather_lanes<MODE>(X.data(), tb, acc.data(), n_mels, u)
+                                                   : gather_phase<MODE>(X.data(), tb, acc.data(), n_mels, u));
+            }
             if (MODE == MODE_MIC) {
                 for (int l = 0; l < 32; ++l) gcc_stage1<R, 0>(EA.data(), EB.data(), X.data(), l);
                 for (int l = 0; l < 32; ++l) gcc_stage2<R, 0>(X.data(), tb, acc.data(), n_mels, l);
@@ -75,7 +80,8 @@ extern "C" int emu_extract(const float* wav, int layout, int n_clips, long long 
     MelPieces mp;
     if (!build_mel_pieces(mel_fb, n_fft / 2 + 1, n_mels, mp).empty()) return -2;
     Tables tb{window, tw_t.data(), lin, reinterpret_cast<const float2*>(mp.w01.data()), mp.endmask.data(), mp.slot0.data(), mp.slot1.data(),
-              mp.pb.data(), mp.ov.data()};
+              mp.pb.data(), mp.ov.data(), mp.lanes_ok ? mp.w4.data() : nullptr, mp.lane_beg.data(), mp.gtab.data(),
+              mp.gather_n[0], mp.gather_n[1]};
 #define GO3(RR, MM, LL) run<RR, MM, LL>(wav, n_clips, L, hop, n_mels, tb, mp.seg_major, T_out, out, clip_max)
 #define GO(RR)                                                                   \
     if (n_fft == 32 * RR) {                                                      \
