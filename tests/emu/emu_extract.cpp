@@ -107,3 +107,17 @@ extern "C" int emu_mel_layout(const float* mel_fb, int n_bins, int n_mels, int* 
     for (int s = 0; s < 64; ++s) ov[s] = mp.ov[s];
     return 0;
 }
+
+// Lane form of the bank (for tests/test_emu_cpu.py::test_mel_lane_form_invariants).
+// info: [lanes_ok, bpt, gather_n0, gather_n1, rec_words, gather_max, zero_rec, spread, modelled gather wavefronts]
+extern "C" int emu_mel_lanes(const float* mel_fb, int n_bins, int n_mels, int* info, int* lane_beg, int* gtab, float* w4) {
+    MelPieces mp;
+    if (!build_mel_pieces(mel_fb, n_bins, n_mels, mp).empty()) return -2;
+    info[0] = mp.lanes_ok ? 1 : 0; info[1] = mp.bpt; info[2] = mp.gather_n[0]; info[3] = mp.gather_n[1];
+    info[4] = kLaneRecWords; info[5] = kLaneGatherMax; info[6] = kLaneZeroRec; info[7] = mp.lane_spread ? 1 : 0;
+    info[8] = mp.lane_gather_wavefronts;
+    for (int l = 0; l < kTeamLanes; ++l) lane_beg[l] = mp.lane_beg[l];
+    for (size_t i = 0; i < mp.gtab.size(); ++i) gtab[i] = mp.gtab[i];
+    for (size_t i = 0; i < mp.w4.size(); ++i) w4[i] = mp.w4[i];
+    return 0;
+}

@@ -123,3 +123,63 @@ def test_mel_piece_layout_invariants(emu, n_fft, sr, n_mels):
             assert all(r == zero_slot or r not in slots for r in reads[len(want):])  # the rest are never-written slots
     else:
         assert slots == list(range(n_pieces))                                       # compact layout: piece index
+
+
+@pytest.mark.parametrize('n_fft,sr,n_mels,bank', [(1024, 24000, 64, 'htk'), (1024, 48000, 64, 'htk'), (1024, 24000, 64, 'tf'),
+                                                    (1024, 24000, 40, 'htk'), (512, 16000, 64, 'htk')])
+def test_mel_lane_form_invariants(emu, n_fft, sr, n_mels, bank):
+    """The flush-free lane form of the bank (csrc/mel_pieces.h build_lane_form): the records the 64 lanes write and the
+    table-driven gather reproduce the dense projection, every lane's reads stay inside the spectrum, the zero record is never
+    a lane's own, and -- for the production banks -- the layout is conflict-free under the shared-memory model it is tuned for."""
+    n_bins = n_fft // 2 + 1
+    if bank == 'htk':
+        fb = np.ascontiguousarray(tables.melscale_fbanks_htk(n_bins, sr, n_mels).numpy())
+    else:
+        fb = np.ascontiguousarray(np.asarray(tables.tf_mel_weight_matrix(n_mels, n_bins, sr), dtype=np.float32))
+    info = np.zeros(16, np.int32)
+    bpt = -(-n_bins // 64)
+    lane_beg, gtab, w4 = np.zeros(64, np.int32), np.zeros(64 * 8, np.int32), np.zeros(64 * bpt * 4, np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert emu.emu_mel_lanes(p(fb), n_bins, n_mels, p(info), p(lane_beg), p(gtab), p(w4)) == 0
+    ok, bpt2, gn0, gn1, rec_words, gmax, zero_rec, spread, modelled = (int(v) for v in info[:9])
+    assert bpt2 == bpt and gmax == 8
+    if n_fft == 1024 and n_mels == 64:
+        assert ok and spread                       # the production banks take the lane form, conflict-free bin reads
+    if not ok:
+        return
+    assert lane_beg.min() >= 0 and lane_beg.max() + bpt <= n_fft         # S[k] and S[N - k] stay inside the n_fft-long spectrum
+    rng = np.random.default_rng(5)
+    val = rng.uniform(0.5, 2.0, n_fft).astype(np.float64)
+    rec = np.zeros((zero_rec + 1) * rec_words)
+    w4 = w4.reshape(64, bpt, 4).astype(np.float64)
+    for u in range(64):
+        for i in range(bpt):
+            k = lane_beg[u] + i
+            if w4[u, i].any():
+                assert k < n_bins
+            rec[u * rec_words:u * rec_words + 4] += w4[u, i] * val[k]
+    gtab = gtab.reshape(64, gmax)
+    assert (gtab < (zero_rec + 1) * rec_words).all()
+    for m in range(n_mels):
+        n = gn0 if m < 32 else gn1
+        assert (gtab[m, n:] == zero_rec * rec_words).all()              # the gather stops at gather_n: nothing may sit past it
+        got = rec[gtab[m, :n]].sum()
+        want = 0.25 * (fb[:, m].astype(np.float64) * val[:n_bins]).sum()
+        assert abs(got - want) <= 1e-12 * max(1.0, abs(want)), (m, got, want)
+    # the shared-memory model: 64-bit reads 16 lanes at a time (bank pair = word pair index mod 16) ...
+    if spread:
+        for g in range(0, 64, 16):
+            assert len({int(b) % 16 for b in lane_beg[g:g + 16]}) == 16
+    # ... 32-bit gather reads 32 lanes at a time, one wavefront per distinct address sharing a bank
+    cost = 0
+    for w, n in ((0, gn0), (1, gn1)):
+        for t in range(n):
+            banks = {}
+            for m in range(32 * w, min(32 * w + 32, n_mels)):
+                a = int(gtab[m, t])
+                if a != zero_rec * rec_words:
+                    banks.setdefault(a % 32, set()).add(a)
+            cost += max([len(v) for v in banks.values()] + [1])
+    assert cost == modelled
+    if n_fft == 1024 and n_mels == 64 and bank == 'htk':
+        assert cost <= gn0 + gn1 + 1
