@@ -519,21 +519,30 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         // Interior frames, software-pipelined: the raw samples of the team's NEXT frame (this warp's channel pair) are
         // requested before the current frame's FFT starts, so HBM/L2 latency hides behind the arithmetic (requesting them
         // later -- after the bin phase -- measured 6 % slower).
-        const long long sc_step = gridDim.x;              // super-chunk sc -> CTA sc mod grid
-        long long sc = blockIdx.x;
-        const long long sc_end = a.n_super;
+        // Frame indices are 32-bit here (launch_one refuses launches of 2^31 frames or more) and (clip, t) of the NEXT frame is
+        // tracked incrementally: one division per run of fpw frames instead of two 64-bit divisions per frame (those and the
+        // 64-bit index products were ~150 of the ~1800 instructions a warp spends on a frame).
+        const int sc_step = gridDim.x;                    // super-chunk sc -> CTA sc mod grid
+        int sc = blockIdx.x;
+        const int sc_end = int(a.n_super);
+        const int n_frames = int(total_frames);
+        const int fpc = a.frames_per_clip;
         int fi = 0;
-        auto frame_index = [&](long long s, int i, int tm) -> long long {       // -1 past the end
-            if (s >= sc_end || tm * a.fpw + i >= a.fsc) return -1;
-            const long long g = s * a.fsc + tm * a.fpw + i;
-            return g < total_frames ? g : -1;
+        int run_base = sc * a.fsc + team * a.fpw;         // frame index of the team's frame fi = 0 of super-chunk sc
+        auto frame_at = [&](int s, int base, int i) -> int {        // -1 past the end
+            return (s < sc_end && base + i < n_frames) ? base + i : -1;
+        };
+        struct Pos { int clip, t; };
+        auto locate = [&](int g) -> Pos {                 // (one 32-bit division: only at the first frame of a run)
+            const int c = int(unsigned(g) / unsigned(fpc));
+            return Pos{c, a.t_lo + (g - c * fpc)};
         };
         float2 raw[R];
         long long start = 0;
         int clip = 0, t = 0;
-        auto request = [&](long long g) {           // issue the loads of frame g (this warp's pair) into raw[]
-            clip = int(g / a.frames_per_clip);
-            t = a.t_lo + int(g - (long long)clip * a.frames_per_clip);
+        auto request_at = [&](Pos p) {              // issue the loads of the frame at (clip, t) (this warp's pair) into raw[]
+            clip = p.clip;
+            t = p.t;
             start = (long long)t * a.hop - G::N / 2 + a.origin;
             if constexpr (LAYOUT == LAYOUT_PCM16_LC) {
                 stage1_load_raw_pcm16_pair<R>(reinterpret_cast<const short*>(a.wav) + (long long)clip * 4 * a.n_samples, h, start, raw, lane);
@@ -546,13 +555,16 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                 stage1_load_raw<R, LAYOUT>(src, 2 * h, 2 * h + 1, start, raw, lane);
             }
         };
+        auto request = [&](int g) { request_at(locate(g)); };
         // FOA at n_fft = 1024 runs four warps per scheduler at 128 registers: the 2R prefetch registers do not fit, the loads
         // are issued at the top of the frame instead and the other warps cover their latency.  Measured alternatives: requesting
         // them after the bin phase spills 376 B (12.3 ms instead of 9.2); staging them through tensor memory four taps per
         // bin step (tcgen05.st, then four tcgen05.ld at the next frame) couples the load latency into the team barriers (10.5 ms)
         constexpr bool PREFETCH = !(R == 32 && (MODE == MODE_FOA || SELD_MIC_WARPS > 12));      // (experiment: MIC at 16 warps has no registers for it either)
-        long long g = frame_index(sc, fi, team);
-        long long gpart = FUSED ? frame_index(sc, fi, pteam) : -1;
+        const int part_off = (pteam - team) * a.fpw;      // the partner team's frames sit fpw further (or back)
+        int g = frame_at(sc, run_base, fi);
+        int gpart = FUSED ? frame_at(sc, run_base + part_off, fi) : -1;
+        Pos next_pos = g >= 0 ? locate(g) : Pos{0, 0};    // (clip, t) of frame g, carried one iteration ahead
         if (PREFETCH && g >= 0) request(g);
         // Consecutive frames share R - 15 taps per lane (hop 480 = 15 * 32 samples: tap n2 of frame t + 1 is tap n2 + 15 of
         // frame t).  The 16-warp kernel parks those 17 taps in its own tensor-memory columns and fetches only the 15 new
@@ -591,9 +603,17 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
 #pragma unroll 1
         while (g >= 0 || gpart >= 0) {
             const bool mine = g >= 0;
-            if (++fi == a.fpw) { fi = 0; sc += sc_step; }
-            const long long g_next = frame_index(sc, fi, team);
-            const long long gpart_next = FUSED ? frame_index(sc, fi, pteam) : -1;
+            const Pos pos = next_pos;
+            if (++fi == a.fpw) { fi = 0; sc += sc_step; run_base += sc_step * a.fsc; }
+            const int g_next = frame_at(sc, run_base, fi);
+            const int gpart_next = FUSED ? frame_at(sc, run_base + part_off, fi) : -1;
+            if constexpr (!PREFETCH) {
+                if (g_next >= 0) {
+                    if (fi == 0 || !mine) next_pos = locate(g_next);
+                    else if (pos.t + 1 == a.t_hi) next_pos = Pos{pos.clip + 1, a.t_lo};
+                    else next_pos = Pos{pos.clip, pos.t + 1};
+                }
+            }
             if constexpr (FUSED) {
                 if (!mine) {                              // only the partner has a frame: help read its accumulator
                     finish_frame(false, true, 0, 0, nullptr, [] {});
@@ -604,8 +624,8 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
             }
             if constexpr (!PREFETCH) {
                 if constexpr (KEEP) {
-                    clip = int(g / a.frames_per_clip);
-                    t = a.t_lo + int(g - (long long)clip * a.frames_per_clip);
+                    clip = pos.clip;
+                    t = pos.t;
                     start = (long long)t * a.hop - G::N / 2 + a.origin;
                     if (keep_ok && clip == prev_clip && t == prev_t + 1) {
                         float* rf = reinterpret_cast<float*>(raw);
@@ -636,7 +656,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                     prev_clip = clip;
                     prev_t = t;
                 } else {
-                    request(g);
+                    request_at(pos);
                 }
             }
             float2 v[R];
@@ -662,8 +682,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                 finish_frame(true, gpart >= 0, clip_now, t_now, row, [&] {
                     if constexpr (BULK) {
                         if (bulk_ok && g_next >= 0 && lane == 0) {
-                            const int c2 = int(g_next / a.frames_per_clip);
-                            const int t2 = a.t_lo + int(g_next - (long long)c2 * a.frames_per_clip);
+                            const int c2 = next_pos.clip, t2 = next_pos.t;
                             const long long s2 = (long long)t2 * a.hop - G::N / 2 + a.origin + 32 * (R - SH);
                             const float* pa = a.wav + ((long long)c2 * 4 + 2 * h) * a.n_samples + s2;
                             const unsigned bar = smem_addr(&s_ldbar[warp]), dst = smem_addr(E);
@@ -676,8 +695,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                         }
                     } else if constexpr (KEEP && kEarlyTail) {
                         if (g_next >= 0) {
-                            const int c2 = int(g_next / a.frames_per_clip);
-                            const int t2 = a.t_lo + int(g_next - (long long)c2 * a.frames_per_clip);
+                            const int c2 = next_pos.clip, t2 = next_pos.t;
                             load_taps(c2, (long long)t2 * a.hop - G::N / 2 + a.origin, R - SH, R, raw);
                         }
                     }
@@ -721,6 +739,10 @@ static int launch_one(const seld_plan* plan, ExtractArgs a, cudaStream_t stream)
     a.fsc = teams * a.fpw;
     const long long per_super = a.fsc;
     a.n_super = ((long long)a.n_clips * a.frames_per_clip + per_super - 1) / per_super;
+    if ((long long)a.n_clips * a.frames_per_clip + (long long)(plan->grid + 1) * per_super >= (1ll << 31)) {
+        set_error("seld_extract: 2^31 or more frames in one launch (split the batch)");      // the kernel indexes frames in 32 bits
+        return SELD_EINVAL;
+    }
     long long grid = a.n_super < plan->grid ? a.n_super : plan->grid;
     static std::atomic<unsigned long long> configured{0};        // bit d: attribute set on device d (per instantiation)
     const unsigned long long bit = 1ull << (plan->device & 63);

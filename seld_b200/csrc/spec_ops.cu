@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128) complex_spec_kernel(const float* __restri
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     float2* s_tw_t = reinterpret_cast<float2*>(smem);
-    unsigned char* wp = smem + sp_align16(G::N * 8) + size_t(warp) * (sp_align16(G::E_ELEMS * 8) + sp_align16(G::N * 8));
+    unsigned char* wp = smem + sp_align16(G::N * 8) + size_t(warp) * (sp_align16(G::E_ELEMS * 8) + sp_align16((G::N + 1) * 8));
     float2* E = reinterpret_cast<float2*>(wp);
     float2* S = reinterpret_cast<float2*>(wp + sp_align16(G::E_ELEMS * 8));
     for (int i = threadIdx.x; i < G::N; i += blockDim.x) s_tw_t[i] = tw_t[i];
@@ -112,7 +112,7 @@ static int launch_spec(const seld_plan* plan, const float* wav, int n_chan, long
                        cudaStream_t st) {
     using G = Geo<R>;
     const int warps = (R == 64) ? 2 : 4;
-    const int smem = sp_align16(G::N * 8) + warps * (sp_align16(G::E_ELEMS * 8) + sp_align16(G::N * 8));
+    const int smem = sp_align16(G::N * 8) + warps * (sp_align16(G::E_ELEMS * 8) + sp_align16((G::N + 1) * 8));
     SELD_CUDA_TRY(cudaFuncSetAttribute(complex_spec_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int t_raw = int(1 + n_samples / plan->hop);
     const long long items = (long long)((n_chan + 1) / 2) * t_raw;
