@@ -414,6 +414,31 @@ def main():
                                    'flight, upload of the next one overlapping the download of the previous one (PCIe is full duplex)',
                             'checksum': float(host_out[0][0, :8].double().sum())}
 
+                def copy_ceiling(host_in, host_o, e2e_ms):
+                    # what the box's host side allows: the SAME bytes moved by plain pinned copies on two streams (upload and
+                    # download concurrently, all ranks at once), no kernels -- the ceiling of any e2e number on this box
+                    d_in = torch.empty(host_in.shape, dtype=host_in.dtype, device=dev)
+                    d_out = torch.empty(host_o.shape, dtype=host_o.dtype, device=dev)
+                    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+                    times = []
+                    for rep in range(3):
+                        barrier()
+                        t0 = time.perf_counter()
+                        with torch.cuda.stream(s_up):
+                            d_in.copy_(host_in, non_blocking=True)
+                        with torch.cuda.stream(s_dn):
+                            host_o.copy_(d_out, non_blocking=True)
+                        s_up.synchronize()
+                        s_dn.synchronize()
+                        times.append(time.perf_counter() - t0)
+                    dt = max_over_ranks([min(times[1:])])[0]
+                    up, dn = host_in.numel() * host_in.element_size() * world, host_o.numel() * host_o.element_size() * world
+                    del d_in, d_out
+                    return {'ms': 1000.0 * dt, 'h2d_GBps_all_ranks': up / dt / 1e9, 'd2h_GBps_all_ranks': dn / dt / 1e9,
+                            'e2e_frac_of_ceiling': 1000.0 * dt / e2e_ms,
+                            'what': 'the same upload + download bytes as plain concurrent pinned cudaMemcpyAsync on every rank at '
+                                    'once, no kernels: the host-side ceiling of this box for the e2e step'}
+
                 # (1) the audio as it sits in the WAV files the reference reads: 16-bit PCM frames [clip, L, 4], decoded on the
                 #     GPU exactly like torchaudio.load (sample / 32768) -- the path's first-class host input
                 host_pcm = torch.empty(ne, L, 4, dtype=torch.int16, pin_memory=True)
@@ -428,6 +453,8 @@ def main():
                 del wav
                 torch.cuda.empty_cache()
                 r = run_e2e(host_pcm, 'interleaved', torch.int16, 'int16 PCM [clip,L,4] (WAV frame order), decoded on the GPU')
+                if mode == 'foa':
+                    r['copy_ceiling'] = copy_ceiling(host_pcm, host_out[0], r['ms_per_step'])
                 del host_pcm
                 if host_f32 is not None:
                     r['float32_input'] = run_e2e(host_f32, 'planar', torch.float32, 'float32 [clip,4,L] (torchaudio.load layout)')
