@@ -186,7 +186,7 @@ def main():
     ap.add_argument('--clips', type=int, default=600, help='clips of the whole job (dev-set shape: 600)')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--cpu-clips', type=int, default=192, help='bounded CPU-baseline sample (full-size clips)')
-    ap.add_argument('--ref-clips', type=int, default=8, help='clips per step of --impl reference')
+    ap.add_argument('--ref-clips', type=int, default=32, help='clips per step of --impl reference')
     ap.add_argument('--layout', default='planar', choices=['planar', 'interleaved'],
                     help="planar [n,4,L] is the reference's (torchaudio.load) layout")
     ap.add_argument('--no-e2e', action='store_true')
