@@ -1,0 +1,2 @@
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2_bench_n8_b.json 2> gpurun_out/r2_bench_n8_b.err
+tail -c 400 gpurun_out/r2_bench_n8_b.err; wc -c gpurun_out/r2_bench_n8_b.json
