@@ -116,6 +116,15 @@ constexpr bool kEarlyTail = SELD_EARLY_TAIL;
 // registers are held across the gather (the early register request above lost to exactly that) and the HBM / L2 latency is off
 // the critical path.  north_star (1)'s "staged through TMA / shared memory", measured: see DESIGN.md 4.1.
 constexpr bool kBulkTail = SELD_BULK_TAIL;
+#ifndef SELD_BULK_MIC
+#define SELD_BULK_MIC 1
+#endif
+// Fused MIC kernel, planar input: it has neither registers for a prefetch nor tensor-memory columns for the shared taps, so the
+// frame's global loads sat exposed at the top of the frame (12 % of the stall samples).  The WHOLE next frame of the warp's channel
+// pair (2 x 4 096 contiguous bytes) is staged by two cp.async.bulk copies into the warp's exchange buffer -- a part of the operand
+// tile, free as soon as the team pair's MMA chain has completed -- issued right after that wait, so the copies run under the GCC
+// epilogue, the pair barrier and the row store, and the frame starts with 64 conflict-free LDS instead of 64 LDG.
+constexpr bool kBulkMic = SELD_BULK_MIC;
 #ifndef SELD_GCC_DEAD
 #define SELD_GCC_DEAD 1
 #endif
@@ -141,7 +150,7 @@ struct SmemPlan {
         return (NEED_TW ? align16(G::N * 8) : 0) + (NEED_W01 ? align16(G::TL * G::BPT * 8) : 0) + align16(G::TL * 8) + 2 * align16(G::TL * 4) +
                align16((n_mels + 2) * 4) + align16(64 * 4) + 16 + (NEED_WIN ? align16(G::N * 4) : 0) + (NEED_TWLIN ? align16(G::N * 8) : 0) +
                (tc ? 64 : 0) +                                          // one mbarrier per frame team
-               ((kBulkTail && MODE == MODE_FOA && R == 32) ? 128 : 0) +  // one mbarrier per warp (bulk-staged tail taps)
+               (((kBulkTail && MODE == MODE_FOA && R == 32) || (kBulkMic && tc)) ? 128 : 0) +  // one mbarrier per warp (bulk-staged taps)
                (lanes ? align16(G::TL * 4) + align16(64 * kLaneGatherMax * 4) : 0);
     }
     __host__ __device__ static constexpr int x_bytes(int n_slots) {
@@ -227,7 +236,8 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     }
     constexpr bool BULK = kBulkTail && MODE == MODE_FOA && R == 32 && !EDGE && LAYOUT == LAYOUT_PLANAR_CL;
     unsigned long long* s_ldbar = nullptr;                                   // bulk-staged tail taps: one mbarrier per warp
-    if constexpr (kBulkTail && MODE == MODE_FOA && R == 32) { s_ldbar = reinterpret_cast<unsigned long long*>(p);  p += 128; }
+    constexpr bool BULKM = kBulkMic && FUSED && !EDGE && LAYOUT == LAYOUT_PLANAR_CL;      // fused MIC: the whole next frame staged
+    if constexpr ((kBulkTail && MODE == MODE_FOA && R == 32) || (kBulkMic && FUSED)) { s_ldbar = reinterpret_cast<unsigned long long*>(p);  p += 128; }
     const float wscale = ((EDGE ? a.layout : LAYOUT) == LAYOUT_PCM16_LC) ? (1.0f / 32768.0f) : 1.0f;    // exact: folds the PCM decode
     for (int i = threadIdx.x; i < G::N; i += blockDim.x) {
         if constexpr (SP::NEED_WIN) s_win[i] = a.window[i] * wscale;
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         s_slot1[threadIdx.x] = a.slot1[threadIdx.x];
         s_ov[threadIdx.x] = a.ov[threadIdx.x];
     }
-    if constexpr (BULK) {
+    if constexpr (BULK || BULKM) {
         if (threadIdx.x < 16) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&s_ldbar[threadIdx.x])));
             asm volatile("fence.mbarrier_init.release.cluster;");
@@ -415,6 +425,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
             mbar_wait_parity(smem_addr(&s_mbar[pair]), par_pair);
             par_pair ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (mine) early();                                           // (the tile is free: the next frame's samples are staged into it)
             {
                 float* mine_row = mine ? acc : nullptr;
                 float* part_row = part ? acc_part : nullptr;
@@ -594,7 +605,8 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         // (kEarlyTail: the SH new taps of the team's NEXT frame requested right after the bin phase)
         bool have_tail = false;                       // every frame but a warp's first gets its tail early
         unsigned ld_parity = 0;
-        const bool bulk_ok = BULK && a.hop % 4 == 0 && a.n_samples % 4 == 0 && a.origin % 4 == 0;      // 16-byte aligned bulk copies
+        const bool bulk_ok = (BULK || BULKM) && a.hop % 4 == 0 && a.n_samples % 4 == 0 && a.origin % 4 == 0;      // 16-byte aligned bulk copies
+        bool staged = false;                          // fused MIC: this frame's samples were staged by the previous iteration
         // (prefetching just the 15 new taps of the next frame in 30 registers was tried on top of this: 104 B of spills and
         //  9.58 ms instead of 9.06)
         // (Fused GCC: deferring a frame's epilogue into the next iteration -- accumulators and staged rows double-buffered, the
@@ -655,6 +667,20 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                     }
                     prev_clip = clip;
                     prev_t = t;
+                } else if constexpr (BULKM) {
+                    if (staged) {
+                        clip = pos.clip;
+                        t = pos.t;
+                        mbar_wait_parity(smem_addr(&s_ldbar[warp]), ld_parity);
+                        ld_parity ^= 1u;
+                        const float* ea = reinterpret_cast<const float*>(E) + lane;
+#pragma unroll
+                        for (int n2 = 0; n2 < R; ++n2) raw[n2] = make_float2(ea[32 * n2], ea[32 * R + 32 * n2]);
+                        __syncwarp();                         // every lane has its taps before anyone's stage-1 store lands in E
+                        staged = false;
+                    } else {
+                        request_at(pos);
+                    }
                 } else {
                     request_at(pos);
                 }
@@ -692,6 +718,22 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                                          :: "r"(dst), "l"(pa), "r"(32 * SH * 4), "r"(bar) : "memory");
                             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                          :: "r"(dst + 32 * SH * 4), "l"(pa + a.n_samples), "r"(32 * SH * 4), "r"(bar) : "memory");
+                        }
+                    } else if constexpr (BULKM) {
+                        if (bulk_ok && g_next >= 0) {
+                            if (lane == 0) {
+                                const int c2 = next_pos.clip, t2 = next_pos.t;
+                                const long long s2 = (long long)t2 * a.hop - G::N / 2 + a.origin;
+                                const float* pa = a.wav + ((long long)c2 * 4 + 2 * h) * a.n_samples + s2;
+                                const unsigned bar = smem_addr(&s_ldbar[warp]), dst = smem_addr(E);
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // E was written through the generic proxy
+                                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2 * G::N * 4) : "memory");
+                                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                             :: "r"(dst), "l"(pa), "r"(G::N * 4), "r"(bar) : "memory");
+                                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                             :: "r"(dst + G::N * 4), "l"(pa + a.n_samples), "r"(G::N * 4), "r"(bar) : "memory");
+                            }
+                            staged = true;
                         }
                     } else if constexpr (KEEP && kEarlyTail) {
                         if (g_next >= 0) {

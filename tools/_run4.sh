@@ -1,0 +1,4 @@
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r2_gputests_4.log
+python tools/time_extract.py mic > gpurun_out/r2_time_mic_v5.log 2>&1
+python tools/time_extract.py foa > gpurun_out/r2_time_foa_v5.log 2>&1
+cat gpurun_out/r2_gputests_4.log gpurun_out/r2_time_mic_v5.log gpurun_out/r2_time_foa_v5.log
