@@ -17,6 +17,13 @@ namespace seld {
 // fixed (mel, chan) columns -- so its clamp mask, mean and 1/std live in registers -- and walks the block's contiguous row
 // slab with UNROLL independent 128-bit loads in flight.  (clip, t) advance incrementally: no division per element.
 constexpr int kUnroll = 4;
+#ifndef SELD_STATS_UNROLL
+#define SELD_STATS_UNROLL 4
+#endif
+#ifndef SELD_STATS_BLOCKS_PER_SM
+#define SELD_STATS_BLOCKS_PER_SM 2      // measured (600 clips, C = 7 | 10): 2 -> 0.611 | 0.865 ms, 4 -> 0.637 | 0.873, 8 -> 0.666 | 0.899; 8 loads in flight: 0.85 | 1.12
+#endif
+constexpr int kStatsUnroll = SELD_STATS_UNROLL;
 
 struct RowCursor {
     long long clip;
@@ -145,13 +152,13 @@ __global__ void __launch_bounds__(512) stats_partial_kernel(const float* __restr
             q[j] = fma(d, d, q[j]);
         }
     };
-    for (; r + (long long)(kUnroll - 1) * rp < r1; r += (long long)kUnroll * rp) {
-        float4 v[kUnroll];
+    for (; r + (long long)(kStatsUnroll - 1) * rp < r1; r += (long long)kStatsUnroll * rp) {
+        float4 v[kStatsUnroll];
         const long long base = r * g4 + g;
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) v[u] = __ldcs(src + base + u * stride4);
+        for (int u = 0; u < kStatsUnroll; ++u) v[u] = __ldcs(src + base + u * stride4);
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
+        for (int u = 0; u < kStatsUnroll; ++u) {
             const float fl = floor_of(keys, cur, t_valid, top_db);
             cur.advance(rp, t_out);
             add(v[u], fl);
@@ -286,7 +293,7 @@ using namespace seld;
 extern "C" {
 
 static int sm_count() { return device_sm_count(); }
-static int stats_block_count() { return sm_count() * 4; }
+static int stats_block_count() { return sm_count() * SELD_STATS_BLOCKS_PER_SM; }
 
 int seld_finalize(int n_mels, int n_ch, const float* feat_in_dev, const uint32_t* clip_max_key_dev, int n_clips, int t_out,
                   int t_valid, float top_db, const float* mean_dev, const float* std_dev, float eps, float* feat_out_dev,
