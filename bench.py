@@ -184,7 +184,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--clips', type=int, default=600, help='clips of the whole job (dev-set shape: 600)')
-    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-steps', type=int, default=8, help='datasets pipelined through the host extractor in the e2e timed region')
     ap.add_argument('--cpu-clips', type=int, default=192, help='bounded CPU-baseline sample (full-size clips)')
     ap.add_argument('--ref-clips', type=int, default=32, help='clips per step of --impl reference')
     ap.add_argument('--layout', default='planar', choices=['planar', 'interleaved'],
