@@ -781,6 +781,8 @@ SELD_HD float gather_records(const float2* P, const Tables& tb, float* acc, int 
     float sum[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) sum[c] = 0.f;
+    // (Two table entries per step with the entries preloaded by two 128-bit loads -- 14 independent record loads in flight -- was
+    //  measured: 8.09 ms per 600 clips against 8.04 for this loop; the other warps already cover the chain's latency.)
     for (int t = 0; t < n; ++t) {
         const float* r = W + gt[t];
 #pragma unroll

@@ -1,2 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2_bench_n8_c.json 2> gpurun_out/r2_bench_n8_c.err
-tail -c 300 gpurun_out/r2_bench_n8_c.err; wc -c gpurun_out/r2_bench_n8_c.json
+python tools/time_extract.py foa > gpurun_out/r2_time_foa_v6.log 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r2_gputests_5.log
+cat gpurun_out/r2_time_foa_v6.log gpurun_out/r2_gputests_5.log
