@@ -605,7 +605,8 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
         // (kEarlyTail: the SH new taps of the team's NEXT frame requested right after the bin phase)
         bool have_tail = false;                       // every frame but a warp's first gets its tail early
         unsigned ld_parity = 0;
-        const bool bulk_ok = (BULK || BULKM) && a.hop % 4 == 0 && a.n_samples % 4 == 0 && a.origin % 4 == 0;      // 16-byte aligned bulk copies
+        const bool bulk_ok = (BULK || BULKM) && a.hop % 4 == 0 && a.n_samples % 4 == 0 && a.origin % 4 == 0 &&
+                             (reinterpret_cast<unsigned long long>(a.wav) & 15ull) == 0;      // 16-byte aligned bulk copies
         bool staged = false;                          // fused MIC: this frame's samples were staged by the previous iteration
         // (prefetching just the 15 new taps of the next frame in 30 registers was tried on top of this: 104 B of spills and
         //  9.58 ms instead of 9.06)

@@ -171,6 +171,32 @@ def test_repeated_launches_are_bit_identical_across_layouts_of_work(mode):
 
 
 @pytest.mark.parametrize('mode', ['foa', 'mic'])
+def test_bulk_staged_loads_equal_the_plain_load_path(mode):
+    """The interior kernels stage the next frame's samples with cp.async.bulk when the input allows 16-byte aligned copies
+    (n_samples % 4 == 0) and fall back to plain loads otherwise.  The same samples through both routes -- clip lengths that
+    are and are not a multiple of four -- must give bit-identical rows."""
+    from seld_b200 import pipeline
+    from seld_b200.synth import make_clips
+    L = 480 * 300
+    wav = make_clips(range(700, 704), L + 4).cuda()
+    aligned = wav[:, :, :L].contiguous()
+    ref, key0 = pipeline.extract_batch(aligned, 24000, mode=mode, **PROD)
+    # (a) a base pointer off a 16-byte boundary is refused at the C ABI (the vector loads and the bulk copies need it)
+    store = torch.empty(aligned.numel() + 1, dtype=torch.float32, device='cuda')
+    shifted = store[1:].view_as(aligned)
+    shifted.copy_(aligned)
+    assert shifted.data_ptr() % 16 == 4
+    with pytest.raises(ValueError):
+        pipeline.extract_batch(shifted, 24000, mode=mode, **PROD)
+    # (b) clip lengths 4k + 1 .. 4k + 3: frames that lie fully inside the shorter clip see the same samples
+    for extra in (1, 2, 3):
+        longer = wav[:, :, :L + extra].contiguous()
+        out, _ = pipeline.extract_batch(longer, 24000, mode=mode, **PROD)
+        t_same = (L - 512) // 480                                              # frames t <= t_same do not reach sample L - 1
+        assert torch.equal(out[:, 2:t_same], ref[:, 2:t_same])
+
+
+@pytest.mark.parametrize('mode', ['foa', 'mic'])
 def test_dev_set_size_properties(mode):
     """BASELINE.json configs[1] / [2] at full size (600 x 60 s clips, 13.8 GB resident) through size-independent properties:
     (1) every copy of a clip in the shard gives bit-identical rows wherever it sits; (2) hop-shift equivariance -- a clip
