@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     // get_preprocessed_x_tf): mel bank on |X|, 20 log10 without a floor, frames from sample 0 with a zero-padded tail
     constexpr bool TFV = (TC & 1) && MODE == MODE_FOA;
     constexpr bool LANES = SP::lanes;
+    constexpr bool PACKED_TW = FUSED;      // fused MIC: packed stage-1 twiddle products + 64-bit exchange stores (extract_core.cuh: cmul_rt_packed)
     // ---- CTA-shared tables
     unsigned char* p = smem;
     float2* s_tw_t = nullptr;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
     auto stage2 = [&]() {
         if constexpr (FUSED) {
             float2 uu[32];
-            stage2_load_fft<R>(E, uu, lane);
+            stage2_load_fft<R, PACKED_TW ? R + 1 : G::EP>(E, uu, lane);
             team_bar(bar_id);
             stage2_store_tile(uu, tile, nyq, lane, h);
         } else {
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
                         else
                             stage1_load_reflect<R>(src, 2 * h, 2 * h + 1, start, wreg, v, lane, TFV);
                         note_dead(v);
-                        if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
+                        if constexpr (TM) stage1_fft_store_tm<R, PACKED_TW>(v, taddr + TMEM_COL_TW, E, lane);
                         else stage1_fft_store<R>(v, tb, E, lane);
                     }
                     __syncwarp();
@@ -702,7 +703,7 @@ __global__ void __launch_bounds__(max_warps<R, MODE>() * 32, 1) extract_kernel(E
             if (PREFETCH && g_next >= 0) request(g_next);
             {
                 note_dead(v);
-                if constexpr (TM) stage1_fft_store_tm<R>(v, taddr + TMEM_COL_TW, E, lane);
+                if constexpr (TM) stage1_fft_store_tm<R, PACKED_TW>(v, taddr + TMEM_COL_TW, E, lane);
                 else stage1_fft_store<R>(v, tb, E, lane);
                 __syncwarp();
                 stage2();

@@ -132,6 +132,14 @@ SELD_HD float2 pcmul(float2 d, float c, float s) {
 SELD_HD float2 cmul_rt(float2 d, float c, float s) {
     return make_float2(fmaf(d.y, -s, d.x * c), fmaf(d.x, s, d.y * c));
 }
+// ... and packed again with c and s as BROADCAST scalar operands and the swap / sign on d's operand modifiers (no pair to build):
+// two issue slots instead of four, same FP32 pipe cycles, same roundings.  The result is an aligned register PAIR, so it wants
+// 64-bit stores (a 128-bit store of two results costs four moves into an aligned quad).  Measured per 600 clips, packed + 64-bit
+// stores at an odd row pitch against scalar + 128-bit stores: MIC 12.90 against 13.21 ms, FOA 8.21 against 8.02 -- each kernel
+// keeps the form that is faster for it (stage1_store_tm's PACKED flag).
+SELD_HD float2 cmul_rt_packed(float2 d, float c, float s) {
+    return pfma(make_float2(-d.y, d.x), make_float2(s, s), pmul(d, make_float2(c, c)));
+}
 
 template <int J, int N>
 SELD_HD float2 pmul_tw(float2 d) {   // d * W_N^J, compile-time twiddle
@@ -323,10 +331,13 @@ __device__ __forceinline__ void tmem_st16(unsigned taddr, const float* r) {
 }
 
 // stage1_fft_store with the twiddles read from tensor memory (same values, same arithmetic as the shared-table version)
-template <int R>
+// PACKED: packed twiddle products and 64-bit stores at row pitch R + 1 float2 (odd: the 16 lanes of a half-warp hit 16 different
+// bank pairs); else scalar products and 128-bit stores at pitch R + 2.  stage2_load_fft takes the same pitch.
+template <int R, bool PACKED = false>
 __device__ __forceinline__ void stage1_store_tm(const float2* v, unsigned taddr_tw, float2* E, int lane) {   // v: pfft_dif output
     using G = Geo<R>;
     static_assert(R % 8 == 0, "twiddles are fetched 8 at a time");
+    constexpr int EPITCH = PACKED ? R + 1 : G::EP;
     float4* E4 = reinterpret_cast<float4*>(E + lane * G::EP);
 #pragma unroll
     for (int g = 0; g < R / 8; ++g) {
@@ -336,16 +347,21 @@ __device__ __forceinline__ void stage1_store_tm(const float2* v, unsigned taddr_
         for (int jj = 0; jj < 4; ++jj) {
             const int j = 4 * g + jj;
             const int p0 = bitrev(2 * j, G::LOG2R), p1 = bitrev(2 * j + 1, G::LOG2R);
-            const float2 a = cmul_rt(v[p0], t[4 * jj], t[4 * jj + 1]), b = cmul_rt(v[p1], t[4 * jj + 2], t[4 * jj + 3]);
-            float4 q; q.x = a.x; q.y = a.y; q.z = b.x; q.w = b.y;
-            E4[j] = q;
+            if constexpr (PACKED) {
+                E[lane * EPITCH + 2 * j] = cmul_rt_packed(v[p0], t[4 * jj], t[4 * jj + 1]);
+                E[lane * EPITCH + 2 * j + 1] = cmul_rt_packed(v[p1], t[4 * jj + 2], t[4 * jj + 3]);
+            } else {
+                const float2 a = cmul_rt(v[p0], t[4 * jj], t[4 * jj + 1]), b = cmul_rt(v[p1], t[4 * jj + 2], t[4 * jj + 3]);
+                float4 q; q.x = a.x; q.y = a.y; q.z = b.x; q.w = b.y;
+                E4[j] = q;
+            }
         }
     }
 }
-template <int R>
+template <int R, bool PACKED = false>
 __device__ __forceinline__ void stage1_fft_store_tm(float2* v, unsigned taddr_tw, float2* E, int lane) {
     pfft_dif<R>(v);
-    stage1_store_tm<R>(v, taddr_tw, E, lane);
+    stage1_store_tm<R, PACKED>(v, taddr_tw, E, lane);
 }
 #endif
 
@@ -363,7 +379,7 @@ SELD_HD void stage1_forward(const ClipSrc& src, int ch_a, int ch_b, long long fr
 // ---------------------------------------------------------------- stage 2: 32-point FFT per column
 // Two per-lane phases so the spectrum can overwrite the exchange buffer (S == E is allowed): every lane first pulls
 // its column(s) into registers and transforms them; after a __syncwarp() the results go back at linear index k.
-template <int R>
+template <int R, int EPITCH = Geo<R>::EP>
 SELD_HD void stage2_load_fft(const float2* E, float2* u, int lane) {      // u[COLS * 32]
     using G = Geo<R>;
 #pragma unroll
@@ -371,7 +387,7 @@ SELD_HD void stage2_load_fft(const float2* E, float2* u, int lane) {      // u[C
         const int k2 = lane + 32 * c;
         if (k2 < R) {
 #pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) u[32 * c + n1] = E[n1 * G::EP + k2];
+            for (int n1 = 0; n1 < 32; ++n1) u[32 * c + n1] = E[n1 * EPITCH + k2];
             pfft_dif<32>(u + 32 * c);
         }
     }
