@@ -495,6 +495,23 @@ SELD_HD void piece_flush(float2* acc, float2* rec, unsigned flag) {
 #endif
 }
 
+#if defined(__CUDACC__)
+// piece_flush for NV = 4 with the record cursor as two shared-memory addresses: if (mask & bit) { store acc to [rec]; acc = 0;
+// rec = nxt; nxt += one record } -- the stores, the clear factor and both cursor updates hang off ONE predicate.
+__device__ __forceinline__ void piece_flush_cursor(float2* acc, unsigned& rec, unsigned& nxt, unsigned mask, unsigned bit) {
+    const unsigned long long* a = reinterpret_cast<const unsigned long long*>(acc);
+    float keep;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %7, %8;\n\tsetp.ne.u32 p, t, 0;\n\t"
+        "@p st.shared.b64 [%1], %3;\n\t@p st.shared.b64 [%1+8], %4;\n\t@p st.shared.b64 [%1+16], %5;\n\t@p st.shared.b64 [%1+24], %6;\n\t"
+        "selp.f32 %0, 0f00000000, 0f3F800000, p;\n\tselp.u32 %1, %2, %1, p;\n\t@p add.u32 %2, %2, 40;\n\t}"
+        : "=f"(keep), "+r"(rec), "+r"(nxt) : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "r"(mask), "r"(bit) : "memory");
+    static_assert(PieceGeo<MODE_MIC>::PSTRIDE * 8 == 40, "record pitch of the MIC pieces");
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = pmul(acc[c], make_float2(keep, keep));
+}
+#endif
+
 SELD_HD float2 pair_phasor(float2 um, float2 un) {   // exp(i angle(conj(Xm) Xn)); angle(0) = 0 -> 1
     const bool zm = (um.x == 0.f && um.y == 0.f), zn = (un.x == 0.f && un.y == 0.f);
     if (zm || zn) return make_float2(1.f, 0.f);
@@ -922,6 +939,16 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
     float2 acc2[NV];
 #pragma unroll
     for (int c = 0; c < NV; ++c) acc2[c] = make_float2(0.f, 0.f);
+    // Integer work hoisted out of the (unrolled) bin loop: bin k = 9u + i sits at tile + 36 k - 32 (k & 3) with (k & 3) = (u + i) & 3,
+    // i.e. at colbase[i & 3] + 36 i -- four per-lane bases, the rest immediate offsets; the record cursor is kept as two
+    // shared-memory addresses advanced under the flush predicate (piece_flush_cursor).  ~15 -> ~6 integer instructions per bin.
+    unsigned char* colbase[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) colbase[j] = tile + 324 * u - 32 * ((u + j) & 3);
+    const bool past = u >= 57;                           // bins 513 .. 575 do not exist: zero weights, no stores, Nyquist column reads
+    const unsigned emask = static_cast<unsigned>(endmask);
+    unsigned rec_addr = static_cast<unsigned>(__cvta_generic_to_shared(P + slot * PSTRIDE));
+    unsigned nxt_addr = static_cast<unsigned>(__cvta_generic_to_shared(P + next * PSTRIDE));
 
     auto spectra = [&](const unsigned char* col, bool real_bin, float2* ch, float* val) {
         float f[8];
@@ -950,7 +977,10 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
     auto step = [&](int i, bool first, bool last) {
         const int k = kbeg + i;
         // bins past N/2 (lanes 57 .. 63) carry zero weights and never close a piece: they read the Nyquist column
-        const unsigned char* col = (k >= N / 2) ? nyq : tile + 36 * k - 32 * (k & 3);
+        // (bin 512 of lane 56 is the Nyquist column by address: it follows the tile)
+        const unsigned char* col;
+        if constexpr (DEAD) col = (k >= N / 2) ? nyq : tile + 36 * k - 32 * (k & 3);
+        else col = past ? nyq : colbase[i & 3] + 36 * i;
         float2 ch[4];
         float val[NV];
         spectra(col, (first && k == 0) || (last && k >= N / 2), ch, val);
@@ -969,7 +999,7 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
 #pragma unroll
                 for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, p[q].y);
             }
-            float* dst = reinterpret_cast<float*>(tile + 36 * k - 32 * (k & 3));
+            float* dst = DEAD ? reinterpret_cast<float*>(tile + 36 * k - 32 * (k & 3)) : reinterpret_cast<float*>(const_cast<unsigned char*>(col));
 #pragma unroll
             for (int q = 0; q < 6; ++q) dst[4 * q] = w[q];
         }
@@ -977,10 +1007,14 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
         tmem_ld2(taddr_w01 + 2 * i, wt.x, wt.y);
 #pragma unroll
         for (int c = 0; c < NV; ++c) acc2[c] = pfma(make_float2(val[c], val[c]), wt, acc2[c]);
-        const unsigned flag = static_cast<unsigned>(endmask >> i) & 1u;
-        piece_flush<NV>(acc2, P + slot * PSTRIDE, flag);
-        slot = flag ? next : slot;
-        next += int(flag);
+        if constexpr (DEAD) {
+            const unsigned flag = static_cast<unsigned>(endmask >> i) & 1u;
+            piece_flush<NV>(acc2, P + slot * PSTRIDE, flag);
+            slot = flag ? next : slot;
+            next += int(flag);
+        } else {
+            piece_flush_cursor(acc2, rec_addr, nxt_addr, emask, 1u << i);
+        }
     };
     if constexpr (DEAD) {
 #pragma unroll 1
