@@ -925,10 +925,9 @@ __device__ __forceinline__ float2 dead_pair(float2 xm, float2 xn, bool dm, bool 
 
 // Bin phase of the fused MIC kernel: powers -> mel pieces as in bin_phase<MODE_MIC>, pair phasors written in place as the
 // B operand.  DEAD (rare, rolled loop): some channel of this frame is exactly zero (dead bits: bit c = channel c).
-// (Measured on top of the broadcast pair products, 600 MIC clips: the channel split as four packed FFMA2 instead of eight scalar
-//  adds 13.87 ms against 13.75 -- the eight 32-bit loads land in unpaired registers; branch-free phasor stores, the lanes past
-//  N/2 dumping into the Nyquist column's unused words, 14.11 ms with 92 B of spills.  Fewer instructions, slower: this kernel
-//  is bound by dependent latency at four warps per scheduler, not by issue slots.)
+// (Measured, 600 MIC clips: the channel split as four packed FFMA2 instead of eight scalar adds 13.87 ms against 13.75 -- the eight
+//  32-bit loads land in unpaired registers.  Instruction cuts pay in this kernel only when they cost no registers: it runs at the
+//  128-register limit with 64 B of spills.)
 template <bool DEAD>
 __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const unsigned char* nyq, const Tables& tb, float2* P, int u,
                                                     unsigned taddr_w01, unsigned dead) {
@@ -986,9 +985,30 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
         spectra(col, (first && k == 0) || (last && k >= N / 2), ch, val);
         float2 p[6];
         phasors(ch, val, p, std::true_type{});           // every lane (the zero fix-up votes); lanes past N/2 compute and drop
-        if (k < N / 2) {
+        if constexpr (DEAD) {
+            if (k < N / 2) {
+                float w[6];
+                if (first && k == 0) {                       // lane 0: the DC and Nyquist bins are real and share word 0 of each row
+                    float2 chn[4], pn[6];
+                    float valn[NV];
+                    spectra(nyq, true, chn, valn);
+                    phasors(chn, valn, pn, std::false_type{});
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, pn[q].x);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, p[q].y);
+                }
+                float* dst = DEAD ? reinterpret_cast<float*>(tile + 36 * k - 32 * (k & 3)) : reinterpret_cast<float*>(const_cast<unsigned char*>(col));
+#pragma unroll
+                for (int q = 0; q < 6; ++q) dst[4 * q] = w[q];
+            }
+        } else {
+            // every lane stores (no branch around the six stores): the lanes without a bin -- 57 .. 63, and lane 56 at bin 512, whose
+            // phasor lane 0 writes -- dump into the unused second word of the Nyquist column's units (12.75 -> 12.59 ms per 600 clips;
+            // the same idea cost 92 B of spills and time before the integer work was hoisted out of this loop)
             float w[6];
-            if (first && k == 0) {                       // lane 0: the DC and Nyquist bins are real and share word 0 of each row
+            if (first && k == 0) {                           // lane 0: the DC and Nyquist bins are real and share word 0 of each row
                 float2 chn[4], pn[6];
                 float valn[NV];
                 spectra(nyq, true, chn, valn);
@@ -999,12 +1019,13 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
 #pragma unroll
                 for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, p[q].y);
             }
-            float* dst = DEAD ? reinterpret_cast<float*>(tile + 36 * k - 32 * (k & 3)) : reinterpret_cast<float*>(const_cast<unsigned char*>(col));
+            const int dump = (last ? (u >= 56) : past) ? 4 : 0;
+            float* dst = reinterpret_cast<float*>(const_cast<unsigned char*>(col) + dump);
 #pragma unroll
             for (int q = 0; q < 6; ++q) dst[4 * q] = w[q];
         }
         float2 wt;
-        tmem_ld2(taddr_w01 + 2 * i, wt.x, wt.y);
+        tmem_ld2(taddr_w01 + 2 * i, wt.x, wt.y);         // (four bins' weights per tcgen05.ld.x8 measured slower: 12.77 against 12.59 ms)
 #pragma unroll
         for (int c = 0; c < NV; ++c) acc2[c] = pfma(make_float2(val[c], val[c]), wt, acc2[c]);
         if constexpr (DEAD) {
