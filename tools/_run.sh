@@ -1,4 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r2_gputests_7.log
-python tools/time_extract.py mic > gpurun_out/r2_time_mic_v7.log 2>&1
-python tools/time_extract.py foa > gpurun_out/r2_time_foa_v8.log 2>&1
-cat gpurun_out/r2_gputests_7.log gpurun_out/r2_time_mic_v7.log gpurun_out/r2_time_foa_v8.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2_bench_n8_d.json 2> gpurun_out/r2_bench_n8_d.err
+tail -c 200 gpurun_out/r2_bench_n8_d.err; wc -c gpurun_out/r2_bench_n8_d.json
