@@ -877,6 +877,7 @@ __device__ __forceinline__ void stage2_store_tile(const float2* u, unsigned char
     for (int p = 0; p < 32; ++p) {
         const int k1 = bitrev(p, 5);
         unsigned char* d = (k1 < 16) ? bd + k1 * GT_CHUNK : (k1 == 16 ? b16 : bm + (31 - k1) * GT_CHUNK);
+        if (k1 == 0 && lane == 0) d = nyq + (4 * h) * 16 + 8;      // Z_h[0] -> third word of the Nyquist column's units (bin_phase_gcc_fused)
         *reinterpret_cast<float*>(d) = u[p].x;
         *reinterpret_cast<float*>(d + 16) = u[p].y;
     }
@@ -977,52 +978,42 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
         const int k = kbeg + i;
         // bins past N/2 (lanes 57 .. 63) carry zero weights and never close a piece: they read the Nyquist column
         // (bin 512 of lane 56 is the Nyquist column by address: it follows the tile)
+        // The DC and the Nyquist bin are real and share word 0 of each row (low / high half).  Lane 0 takes DC in its first step --
+        // its spectrum sits in the third words of the Nyquist column's units, so that bin 0's words are write-only here -- and lane
+        // 63, which has no bins, takes the Nyquist bin in ITS first step: both store 16-bit halves.  (Lane 0 used to compute both
+        // in a divergent block of ~60 instructions that the team's other warp waited for at the barrier.)
+        const bool dc = first && k == 0, ny = first && u == 63;
         const unsigned char* col;
         if constexpr (DEAD) col = (k >= N / 2) ? nyq : tile + 36 * k - 32 * (k & 3);
         else col = past ? nyq : colbase[i & 3] + 36 * i;
+        if (dc) col = nyq + 8;
         float2 ch[4];
         float val[NV];
-        spectra(col, (first && k == 0) || (last && k >= N / 2), ch, val);
+        spectra(col, dc || ny || (last && k >= N / 2), ch, val);
         float2 p[6];
         phasors(ch, val, p, std::true_type{});           // every lane (the zero fix-up votes); lanes past N/2 compute and drop
+        float w[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, p[q].y);
         if constexpr (DEAD) {
-            if (k < N / 2) {
-                float w[6];
-                if (first && k == 0) {                       // lane 0: the DC and Nyquist bins are real and share word 0 of each row
-                    float2 chn[4], pn[6];
-                    float valn[NV];
-                    spectra(nyq, true, chn, valn);
-                    phasors(chn, valn, pn, std::false_type{});
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, pn[q].x);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, p[q].y);
-                }
-                float* dst = DEAD ? reinterpret_cast<float*>(tile + 36 * k - 32 * (k & 3)) : reinterpret_cast<float*>(const_cast<unsigned char*>(col));
+            if (k < N / 2 && !dc) {
+                float* dst = reinterpret_cast<float*>(tile + 36 * k - 32 * (k & 3));
 #pragma unroll
                 for (int q = 0; q < 6; ++q) dst[4 * q] = w[q];
             }
         } else {
-            // every lane stores (no branch around the six stores): the lanes without a bin -- 57 .. 63, and lane 56 at bin 512, whose
-            // phasor lane 0 writes -- dump into the unused second word of the Nyquist column's units (12.75 -> 12.59 ms per 600 clips;
-            // the same idea cost 92 B of spills and time before the integer work was hoisted out of this loop)
-            float w[6];
-            if (first && k == 0) {                           // lane 0: the DC and Nyquist bins are real and share word 0 of each row
-                float2 chn[4], pn[6];
-                float valn[NV];
-                spectra(nyq, true, chn, valn);
-                phasors(chn, valn, pn, std::false_type{});
-#pragma unroll
-                for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, pn[q].x);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) w[q] = pack_half2(p[q].x, p[q].y);
-            }
+            // every lane stores (no branch around the six stores): the lanes without a bin -- 57 .. 63, and lane 56 at bin 512 --
+            // dump into the unused second word of the Nyquist column's units, lane 0's DC step over the words it has just read
+            // (12.75 -> 12.59 ms per 600 clips; the same idea cost 92 B of spills and time before the integer work was hoisted)
             const int dump = (last ? (u >= 56) : past) ? 4 : 0;
             float* dst = reinterpret_cast<float*>(const_cast<unsigned char*>(col) + dump);
 #pragma unroll
             for (int q = 0; q < 6; ++q) dst[4 * q] = w[q];
+        }
+        if (dc || ny) {
+            unsigned short* d16 = reinterpret_cast<unsigned short*>(tile + (ny ? 2 : 0));
+#pragma unroll
+            for (int q = 0; q < 6; ++q) d16[8 * q] = static_cast<unsigned short>(__float_as_uint(w[q]) & 0xffffu);     // fp16(Re)
         }
         float2 wt;
         tmem_ld2(taddr_w01 + 2 * i, wt.x, wt.y);         // (four bins' weights per tcgen05.ld.x8 measured slower: 12.77 against 12.59 ms)
