@@ -913,6 +913,20 @@ __device__ __forceinline__ void pair_phasors(const float2* ch, const float* val,
     }
 }
 
+// ... and without any fix-up: a pair with a zero (underflowing) channel comes out non-finite -- rsqrt.ftz gives +inf -- and the
+// caller patches the packed words after its bin loop, behind ONE vote on the smallest power it has seen (bin_phase_gcc_fused).
+__device__ __forceinline__ void pair_phasors_raw(const float2* ch, const float* val, float2* p) {
+    float2 uc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float inv = rsqrt_ftz(val[c]);
+        uc[c] = pmul(ch[c], make_float2(inv, inv));
+    }
+    constexpr int PM[6] = {0, 0, 0, 1, 1, 2}, PN[6] = {1, 2, 3, 2, 3, 3};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) p[q] = unit_pair(uc[PM[q]], uc[PN[q]], false);
+}
+
 // The reference on a DEAD channel (an exactly zero spectrum): R = conj(X_m) X_n is a signed zero, torch.angle gives pi where
 // its real part is -0 -- which is where the live partner has Re < 0 and Im < 0 (sign bits; measured on the reference's torch
 // build for either operand order) -- and exp(1j * pi) = (-1, -8.74e-8) in complex64.  Two dead channels give +0 -> 1.
@@ -966,7 +980,14 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
 #pragma unroll
         for (int c = 0; c < 4; ++c) val[c] = fmaf(ch[c].x, ch[c].x, ch[c].y * ch[c].y);
     };
+    unsigned vmin = 0x7f800000u;                         // smallest power seen, as its bit pattern (powers are >= +0, or NaN: not small)
     auto phasors = [&](const float2* ch, const float* val, float2* p, auto vote) {
+        if constexpr (!DEAD) {
+            // live frames: no per-bin zero test.  A bin with a zero channel is rare; its words are patched after the loop
+            pair_phasors_raw(ch, val, p);
+            vmin = min(min(vmin, min(__float_as_uint(val[0]), __float_as_uint(val[1]))), min(__float_as_uint(val[2]), __float_as_uint(val[3])));
+            return;
+        }
         pair_phasors<decltype(vote)::value>(ch, val, p);
         if constexpr (DEAD) {
             constexpr int PM[6] = {0, 0, 0, 1, 1, 2}, PN[6] = {1, 2, 3, 2, 3, 3};
@@ -1034,6 +1055,25 @@ __device__ __forceinline__ void bin_phase_gcc_fused(unsigned char* tile, const u
     } else {
 #pragma unroll
         for (int i = 0; i < BPT; ++i) step(i, i == 0, i == BPT - 1);
+        // rare: some lane of the warp met a power below FLT_MIN (the test the per-bin fix-up made: a pair with such a channel is
+        // exp(i angle(0)) = 1).  Its words hold inf / NaN halves; every lane rescans its own words.
+        if (__any_sync(0xffffffffu, vmin < 0x00800000u)) {
+            auto bad = [](unsigned h) { return (h & 0x7c00u) == 0x7c00u; };
+#pragma unroll 1
+            for (int i = 0; i < BPT; ++i) {
+                const int k = kbeg + i;
+                if (k >= N / 2) break;
+                if (k == 0) continue;                    // (bin 0's words are patched half by half below)
+                unsigned* w = reinterpret_cast<unsigned*>(tile + 36 * k - 32 * (k & 3));
+#pragma unroll 1
+                for (int q = 0; q < 6; ++q) if (bad(w[4 * q]) || bad(w[4 * q] >> 16)) w[4 * q] = 0x00003c00u;      // (1, 0)
+            }
+            if (u == 0 || u == 63) {                     // DC (low halves) / Nyquist (high halves): real, 1 where a channel is zero
+                unsigned short* d16 = reinterpret_cast<unsigned short*>(tile + (u ? 2 : 0));
+#pragma unroll 1
+                for (int q = 0; q < 6; ++q) if (bad(d16[8 * q])) d16[8 * q] = 0x3c00u;
+            }
+        }
     }
 }
 
