@@ -18,7 +18,9 @@ normalise (a8).  The line carries BASELINE.json's configs:
 `value` = audio-hours/s of the whole job with inputs resident in HBM, the step replayed as ONE CUDA graph (`graph`);
 `roofline` = the extract kernel's algorithmic bytes / its CUDA-event time against the measured HBM copy peak; `e2e` =
 the same metric through pipeline.HostDatasetExtractor with pinned HOST buffers (H2D of every clip, D2H of every feature
-inside the timed region); `cpu_baseline` = the oracle port of the reference's CPU path on this box's host cores.
+inside the timed region, `--e2e-steps` datasets pipelined); `e2e.copy_ceiling` = the same upload + download bytes as plain
+concurrent pinned copies on every rank at once, no kernels -- what the host side of the box allows, measured in the same run;
+`cpu_baseline` = the oracle port of the reference's CPU path on this box's host cores.
 """
 import argparse
 import json
