@@ -3,7 +3,7 @@
 // (LOP3 on the ALU pipe, LDS on the LSU, MOV).  If fillers are free up to 8 per iteration, FFMA2 leaves its second cycle to
 // them and the extractor's floor is max(issue slots, FP32 pipe cycles); if time grows from the first filler on, packed
 // instructions hold the issue port for both cycles and the floor is issue slots + packed instructions.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 coissue.cu -o coissue && ./coissue
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared coissue.cu -o coissue && ./coissue
 #include <cstdio>
 #include <cuda_runtime.h>
 

@@ -1,5 +1,5 @@
 // Micro-benchmark: issue rate of packed FFMA2 vs scalar FFMA on sm_100a (decides whether the FFT butterflies
-// should use add/mul/fma.f32x2).  nvcc -gencode arch=compute_100a,code=sm_100a -O3 f32x2.cu -o f32x2 && ./f32x2
+// should use add/mul/fma.f32x2).  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared f32x2.cu -o f32x2 && ./f32x2
 #include <cstdio>
 #include <cuda_runtime.h>
 
